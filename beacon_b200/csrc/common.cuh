@@ -1,0 +1,191 @@
+// Shared device/host helpers for the beacon_b200 kernels (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cmath>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/beacon_b200.h"
+
+namespace beacon {
+
+// ---------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+
+#define BEACON_CUDA_CHECK(expr)                                                                  \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess)                                                                   \
+            throw ::beacon::Error(BEACON_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+#define BEACON_REQUIRE(cond, msg)                                        \
+    do {                                                                 \
+        if (!(cond)) throw ::beacon::Error(BEACON_ERR_INVALID, (msg));   \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------
+// device math helpers
+// ---------------------------------------------------------------------------------------
+template <typename R> struct real_traits;
+template <> struct real_traits<double> { static constexpr int dtype = BEACON_F64; };
+template <> struct real_traits<float> { static constexpr int dtype = BEACON_F32; };
+
+// numpy maximum/minimum: NaN from either argument propagates (CUDA fmin/fmax drop it).
+template <typename R> __device__ __forceinline__ R np_max(R a, R b) { return (a != a) ? a : (a > b ? a : b); }
+template <typename R> __device__ __forceinline__ R np_min(R a, R b) { return (a != a) ? a : (a < b ? a : b); }
+
+template <typename R> __device__ __forceinline__ R rabs(R x);
+template <> __device__ __forceinline__ double rabs(double x) { return fabs(x); }
+template <> __device__ __forceinline__ float rabs(float x) { return fabsf(x); }
+template <typename R> __device__ __forceinline__ R rsqrt_(R x);
+template <> __device__ __forceinline__ double rsqrt_(double x) { return sqrt(x); }
+template <> __device__ __forceinline__ float rsqrt_(float x) { return sqrtf(x); }
+
+template <typename R> __device__ __forceinline__ bool finite_(R x) { return isfinite(x); }
+
+template <typename T> __device__ __forceinline__ T warp_sum(T v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Deterministic block-wide sum: warp shuffles, then the warp partials are added in warp order
+// by every thread (same order everywhere -> identical result in all threads).
+// `scratch` needs blockDim.x/32 entries; contains two barriers.
+template <typename T> __device__ __forceinline__ T block_sum(T v, T *scratch)
+{
+    v = warp_sum(v);
+    const int nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    T r = scratch[0];
+    for (int w = 1; w < nw; w++) r += scratch[w];
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------
+// Philox4x32-10 counter-based RNG (Salmon et al. 2011).  One call -> 4 x 32 random bits.
+// Counter = (draw index lo/hi, global env index lo/hi), key = seed: the noise an env sees
+// depends only on (seed, global env index, draw index), never on batch size or sharding.
+// ---------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1)
+{
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)M0 * c[0], p1 = (uint64_t)M1 * c[2];
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1, n3 = (uint32_t)p0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+        k0 += W0; k1 += W1;
+    }
+}
+
+// U(-sigma, sigma) from (seed, env, draw): 53-bit mantissa uniform in [0,1).
+__host__ __device__ __forceinline__ double philox_uniform_pm(uint64_t seed, uint64_t env, uint64_t draw, double sigma)
+{
+    uint32_t c[4] = {(uint32_t)draw, (uint32_t)(draw >> 32), (uint32_t)env, (uint32_t)(env >> 32)};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    uint64_t bits = (((uint64_t)c[0] << 32) | c[1]) >> 11;
+    double u = (double)bits * (1.0 / 9007199254740992.0);
+    return -sigma + 2.0 * sigma * u;
+}
+
+// ---------------------------------------------------------------------------------------
+// host-side env base: owns device buffers, exposes named state fields
+// ---------------------------------------------------------------------------------------
+struct DeviceBuffer {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+    DeviceBuffer() = default;
+    DeviceBuffer(const DeviceBuffer &) = delete;
+    DeviceBuffer &operator=(const DeviceBuffer &) = delete;
+    ~DeviceBuffer() { if (ptr) cudaFree(ptr); }
+    void alloc(size_t n)
+    {
+        if (ptr) { cudaFree(ptr); ptr = nullptr; }
+        bytes = n;
+        if (n) {
+            BEACON_CUDA_CHECK(cudaMalloc(&ptr, n));
+            BEACON_CUDA_CHECK(cudaMemset(ptr, 0, n));
+        }
+    }
+    template <typename T> T *as() const { return static_cast<T *>(ptr); }
+};
+
+struct Field {
+    std::string name;
+    void *ptr;          // device pointer, [batch, count] contiguous
+    int64_t count;      // elements per env
+    int elem_bytes;     // 8/4 real, 4 int32
+    bool is_int;
+};
+
+struct StepArgs {
+    const void *actions; const void *noise; void *obs; void *rwd; uint8_t *done; uint8_t *trunc;
+    int32_t *status; int64_t *iters; int32_t n_fused; cudaStream_t stream;
+};
+struct ResetArgs {
+    const uint8_t *mask; const int32_t *n_warm; const void *noise; int32_t max_warm; void *obs; cudaStream_t stream;
+};
+
+class Env {
+public:
+    beacon_common common{};
+    beacon_env_info_t info{};
+    std::vector<Field> fields;
+    int64_t launches = 0;
+    // host staging buffers for step_host
+    DeviceBuffer d_act, d_noise, d_obs, d_rwd, d_done, d_trunc, d_status;
+
+    virtual ~Env() {}
+    virtual void reset(const ResetArgs &a) = 0;
+    virtual void step(const StepArgs &a) = 0;
+
+    int real_bytes() const { return info.dtype == BEACON_F64 ? 8 : 4; }
+    const Field *find(const char *name) const
+    {
+        for (auto &f : fields) if (f.name == name) return &f;
+        return nullptr;
+    }
+    void add_field(const char *name, void *ptr, int64_t count, bool is_int = false)
+    {
+        fields.push_back(Field{name, ptr, count, is_int ? 4 : real_bytes(), is_int});
+        info.n_fields = (int32_t)fields.size();
+    }
+    void step_host(const void *actions, const void *noise, void *obs, void *rwd, uint8_t *done, uint8_t *trunc,
+                   int32_t *status, cudaStream_t stream);
+};
+
+// upload a host float64 array as `R`
+template <typename R> inline void upload_as(DeviceBuffer &dst, const double *src, size_t n)
+{
+    std::vector<R> tmp(n);
+    for (size_t i = 0; i < n; i++) tmp[i] = (R)src[i];
+    dst.alloc(n * sizeof(R));
+    BEACON_CUDA_CHECK(cudaMemcpy(dst.ptr, tmp.data(), n * sizeof(R), cudaMemcpyHostToDevice));
+}
+
+// factories implemented in the per-env translation units
+Env *make_shkadov(const beacon_common &, const beacon_shkadov_params &, const double *h_init, const double *q_init);
+Env *make_burgers(const beacon_common &, const beacon_burgers_params &);
+Env *make_sloshing(const beacon_common &, const beacon_sloshing_params &, const double *h_init, const double *q_init);
+Env *make_lorenz(const beacon_common &, const beacon_lorenz_params &);
+Env *make_vortex(const beacon_common &, const beacon_vortex_params &);
+Env *make_mac(const beacon_common &, const beacon_mac_params &, int kind, const double *u0, const double *v0,
+              const double *p0, const double *s0);
+
+}  // namespace beacon

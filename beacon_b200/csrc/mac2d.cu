@@ -1,0 +1,531 @@
+// rayleigh-v0 and mixing-v0 — 2D incompressible flow on a MAC staggered grid, Chorin projection
+// with the reference's own Jacobi pressure iteration, scalar (temperature / concentration)
+// transport, probe history and reward.
+//
+// Reference: /root/reference/beacon/rayleigh/rayleigh.py — solve() :160-240, predictor :371-407,
+// poisson :412-456, corrector :461-464, transport :469-487, get_obs :243-262, get_rwd :265-275;
+// /root/reference/beacon/mixing/mixing.py — solve() :136-209, get_control :212-234,
+// predictor :382-416, poisson :421-465, corrector :470-473, transport :478-495,
+// get_obs :237-256, get_rwd :259-264.
+//
+// B200 design: ONE CTA PER ENVIRONMENT runs every sub-step of every fused action without
+// returning to the host.
+//   * each thread owns a TI x TJ tile of cells (TJ contiguous in y); the Poisson right-hand side
+//     of its tile stays in REGISTERS for the whole solve, phi ping-pongs between two
+//     shared-memory planes, so a Jacobi sweep is: halo loads, ~9 flops per cell, one store,
+//     a warp-shuffle residual reduction and ONE __syncthreads; all threads evaluate the same
+//     residual sum in the same order, so the data-dependent `while err > tol` is uniform;
+//   * the residual reproduces the reference's: sum over the whole ghost-inclusive array after
+//     the ghost update (ghost copies re-count the wall-adjacent cells; mixing's top ghost is 0);
+//   * the in-place lexicographic transport sweep (a Gauss-Seidel-like dependence on the new
+//     west/south neighbours) is split in two: all threads pre-compute, per cell, the part of the
+//     update that only involves OLD values plus the two coefficients multiplying the new
+//     neighbours; then one warp runs the remaining 2-FMA recurrence as a skewed wavefront, rows
+//     across lanes, the new west value travelling by warp shuffle (no barriers);
+//   * rayleigh (50x50): all eight planes live in shared memory (173 KB fp64); mixing (100x100,
+//     83 KB per plane): phi planes in shared memory, the other planes stay in L2-resident global
+//     memory (Poisson dominates: ~21 k sweeps per action vs 250 predictor/transport passes).
+#include "common.cuh"
+
+namespace beacon {
+
+#define MAC_RPL 2   // rows per lane in the transport wavefront
+
+template <typename R> struct MacArgs {
+    int nx, ny, ld, n, ndt_act, n_act, kind, n_sgts, nx_sgts, itmax, tiles_i, tiles_j;
+    int nx_obs_pts, ny_obs_pts, n_obs_steps, nx_obs, ny_obs, n_obs, tr_pass;
+    R dx, dy, dt, inv_dx, inv_dy, inv_dx2, inv_dy2, dx2, dy2, inv_den, cscale, dcoef, tcoef, Tc, Th, Cmax, u_max, ref_c, tol;
+    int B, mode, n_fused;
+    R *u, *v, *p, *s, *us, *vs, *cc;   // [B, n] planes (s = T or C); us/vs/cc are workspaces
+    R *a_cur, *obs_hist;
+    int32_t *stp, *a_int;
+    const R *u0, *v0, *p0, *s0;
+    const void *actions;
+    const uint8_t *mask;
+    R *obs, *rwd;
+    uint8_t *done, *trunc;
+    int32_t *status;
+    int64_t *iters;
+};
+
+// numpy pairwise sum for n <= 128 (np.mean of the action vector, rayleigh.py:165)
+template <typename R> __device__ R np_pairwise_small(const R *a, int n)
+{
+    if (n < 8) {
+        R res = R(0);
+        for (int i = 0; i < n; i++) res += a[i];
+        return res;
+    }
+    R r[8];
+    int i;
+    for (i = 0; i < 8; i++) r[i] = a[i];
+    for (i = 8; i < n - (n % 8); i += 8)
+        for (int k = 0; k < 8; k++) r[k] += a[i + k];
+    R res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; i++) res += a[i];
+    return res;
+}
+
+template <typename R, int TI, int TJ, int T, bool SMEM>
+__global__ void __launch_bounds__(T) mac_kernel(const MacArgs<R> a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ R s_part[2][T / 32];
+    __shared__ R s_red[T / 32];
+    __shared__ R s_seg[128];          // Th + a_j per segment (rayleigh) / wall speeds (mixing)
+    __shared__ R s_act[128];
+    const int tid = threadIdx.x, b = blockIdx.x;
+    const int nx = a.nx, ny = a.ny, ld = a.ld, n = a.n;
+    const bool resetting = a.mode == 1;
+    if (resetting && a.mask && !a.mask[b]) return;
+    const bool ray = a.kind == BEACON_RAYLEIGH;
+
+    // ---- planes ------------------------------------------------------------------------------
+    R *phiA = reinterpret_cast<R *>(smem_raw), *phiB = phiA + n;
+    R *u, *v, *p, *s, *us, *vs;
+    const size_t row = (size_t)b * n;
+    if (SMEM) { u = phiB + n; v = u + n; p = v + n; s = p + n; us = s + n; vs = us + n; }
+    else { u = a.u + row; v = a.v + row; p = a.p + row; s = a.s + row; us = a.us + row; vs = a.vs + row; }
+    R *gu = a.u + row, *gv = a.v + row, *gp = a.p + row, *gs = a.s + row;
+
+    // ---- tile ownership ------------------------------------------------------------------------
+    const bool has_tile = tid < a.tiles_i * a.tiles_j;
+    const int ti = tid / a.tiles_j, tj = tid - ti * a.tiles_j;
+    const int i0 = 1 + ti * TI, j0 = 1 + tj * TJ;
+#define CELL_LOOP                                       \
+    _Pragma("unroll") for (int r = 0; r < TI; r++)      \
+    _Pragma("unroll") for (int k = 0; k < TJ; k++)
+#define CELL_OK(i, j) (has_tile && (i) <= nx && (j) <= ny)
+
+    // ---- load / reset ----------------------------------------------------------------------------
+    if (resetting) {
+        for (int e = tid; e < n; e += T) {
+            R uu = ray ? a.u0[e] : R(0), vv = ray ? a.v0[e] : R(0), pp = ray ? a.p0[e] : R(0), ss = a.s0[e];
+            gu[e] = uu; gv[e] = vv; gp[e] = pp; gs[e] = ss;
+            a.us[row + e] = R(0); a.vs[row + e] = R(0);
+            if (SMEM) { u[e] = uu; v[e] = vv; s[e] = ss; }
+        }
+        for (int e = tid; e < a.n_obs; e += T) a.obs_hist[(size_t)b * a.n_obs + e] = R(0);
+        for (int e = tid; e < (ray ? a.n_sgts : 0); e += T) a.a_cur[(size_t)b * a.n_sgts + e] = R(0);
+        if (tid == 0) { a.stp[b] = 0; if (!ray) a.a_int[b] = 1; }
+        __syncthreads();
+    } else if (SMEM) {
+        for (int e = tid; e < n; e += T) { u[e] = gu[e]; v[e] = gv[e]; p[e] = gp[e]; s[e] = gs[e]; us[e] = a.us[row + e]; vs[e] = a.vs[row + e]; }
+        __syncthreads();
+    }
+    for (int e = tid; e < 2 * n; e += T) phiA[e] = R(0);
+    int stp = resetting ? 0 : a.stp[b];
+    int status = 0;
+    const int n_actions = resetting ? 0 : a.n_fused;
+
+    for (int act = 0; act < n_actions; act++) {
+        const size_t orow = (size_t)act * a.B + b;
+        __syncthreads();
+        // ---- action conditioning ----------------------------------------------------------------
+        if (ray) {
+            const R *ain = (const R *)a.actions + orow * a.n_sgts;
+            if (tid == 0) {                                        // rayleigh.py:164-171
+                const int ns = a.n_sgts;
+                for (int j = 0; j < ns; j++) s_act[j] = ain[j];
+                R mean = np_pairwise_small(s_act, ns) / R(ns);
+                R m = R(1);
+                for (int j = 0; j < ns; j++) { s_act[j] = s_act[j] - mean; m = np_max(m, rabs(s_act[j]) / a.Cmax); }
+                for (int j = 0; j < ns; j++) { s_act[j] = s_act[j] / m; s_seg[j] = a.Th + s_act[j]; a.a_cur[(size_t)b * ns + j] = s_act[j]; }
+            }
+        } else if (tid == 0) {                                     // get_control, mixing.py:212-234
+            int ai = ((const int32_t *)a.actions)[orow];
+            R ut = 0, ub = 0, vl = 0, vr = 0;
+            if (ai == 0) { ub = a.u_max; ut = -a.u_max; }
+            if (ai == 1) { ub = -a.u_max; ut = a.u_max; }
+            if (ai == 2) { vr = a.u_max; vl = -a.u_max; }
+            if (ai == 3) { vr = -a.u_max; vl = a.u_max; }
+            s_seg[0] = ut; s_seg[1] = ub; s_seg[2] = vl; s_seg[3] = vr;
+            a.a_int[b] = ai;
+        }
+        __syncthreads();
+        long long it_total = 0;
+
+        for (int it = 0; it < a.ndt_act; it++) {
+            // ---- boundary conditions: rayleigh.py:180-202, mixing.py:153-171 ---------------------
+            // (wall-normal velocities are zeroed first in the reference; the ghost formulas below
+            //  read them as zero, so one pass suffices)
+            for (int k = tid; k < 2 * (nx + 2) + 2 * (ny + 2); k += T) {
+                if (k < ny + 2) {                                  // left wall (i = 0/1), index j = k
+                    int j = k;
+                    if (j >= 1 && j <= ny) { u[1 * ld + j] = R(0); s[0 * ld + j] = s[1 * ld + j]; }
+                    if (j >= 2 && j <= ny) v[0 * ld + j] = ray ? -v[1 * ld + j] : R(2) * s_seg[2] - v[1 * ld + j];
+                } else if (k < 2 * (ny + 2)) {                     // right wall
+                    int j = k - (ny + 2);
+                    if (j >= 1 && j <= ny) { u[(nx + 1) * ld + j] = R(0); s[(nx + 1) * ld + j] = s[nx * ld + j]; }
+                    if (j >= 2 && j <= ny) v[(nx + 1) * ld + j] = ray ? -v[nx * ld + j] : R(2) * s_seg[3] - v[nx * ld + j];
+                } else if (k < 2 * (ny + 2) + (nx + 2)) {          // top wall (j = ny+1), index i
+                    int i = k - 2 * (ny + 2);
+                    if (i >= 1 && i <= nx + 1) {
+                        R ui = (i == 1 || i == nx + 1) ? R(0) : u[i * ld + ny];
+                        u[i * ld + ny + 1] = ray ? -ui : R(2) * s_seg[0] - ui;
+                    }
+                    if (i >= 1 && i <= nx) {
+                        v[i * ld + ny + 1] = R(0);
+                        s[i * ld + ny + 1] = ray ? R(2) * a.Tc - s[i * ld + ny] : s[i * ld + ny];
+                    }
+                } else {                                           // bottom wall (j = 0/1)
+                    int i = k - 2 * (ny + 2) - (nx + 2);
+                    if (i >= 1 && i <= nx + 1) {
+                        R ui = (i == 1 || i == nx + 1) ? R(0) : u[i * ld + 1];
+                        u[i * ld + 0] = ray ? -ui : R(2) * s_seg[1] - ui;
+                    }
+                    if (i >= 1 && i <= nx) {
+                        v[i * ld + 1] = R(0);
+                        if (ray) {
+                            int sg = (i - 1) / a.nx_sgts;
+                            if (sg < a.n_sgts) s[i * ld + 0] = R(2) * s_seg[sg] - s[i * ld + 1];
+                        } else s[i * ld + 0] = s[i * ld + 1];
+                    }
+                }
+            }
+            __syncthreads();
+
+            // ---- predictor: rayleigh.py:371-407, mixing.py:382-416 ------------------------------------
+            CELL_LOOP {
+                const int i = i0 + r, j = j0 + k;
+                if (CELL_OK(i, j)) {
+                    const R uc = u[i * ld + j], vc = v[i * ld + j];
+                    if (i >= 2) {
+                        R uE = R(0.5) * (u[(i + 1) * ld + j] + uc), uW = R(0.5) * (uc + u[(i - 1) * ld + j]);
+                        R uN = R(0.5) * (u[i * ld + j + 1] + uc), uS = R(0.5) * (uc + u[i * ld + j - 1]);
+                        R vN = R(0.5) * (v[i * ld + j + 1] + v[(i - 1) * ld + j + 1]), vS = R(0.5) * (vc + v[(i - 1) * ld + j]);
+                        R conv = (uE * uE - uW * uW) * a.inv_dx + (uN * vN - uS * vS) * a.inv_dy;
+                        R diff = ((u[(i + 1) * ld + j] - R(2) * uc + u[(i - 1) * ld + j]) * a.inv_dx2 +
+                                  (u[i * ld + j + 1] - R(2) * uc + u[i * ld + j - 1]) * a.inv_dy2) * a.dcoef;
+                        R pres = (p[i * ld + j] - p[(i - 1) * ld + j]) * a.inv_dx;
+                        us[i * ld + j] = uc + a.dt * (diff - conv - pres);
+                    }
+                    if (j >= 2) {
+                        R vE = R(0.5) * (v[(i + 1) * ld + j] + vc), vW = R(0.5) * (vc + v[(i - 1) * ld + j]);
+                        R uE = R(0.5) * (u[(i + 1) * ld + j] + u[(i + 1) * ld + j - 1]), uW = R(0.5) * (uc + u[i * ld + j - 1]);
+                        R vN = R(0.5) * (v[i * ld + j + 1] + vc), vS = R(0.5) * (vc + v[i * ld + j - 1]);
+                        R conv = (uE * vE - uW * vW) * a.inv_dx + (vN * vN - vS * vS) * a.inv_dy;
+                        R diff = ((v[(i + 1) * ld + j] - R(2) * vc + v[(i - 1) * ld + j]) * a.inv_dx2 +
+                                  (v[i * ld + j + 1] - R(2) * vc + v[i * ld + j - 1]) * a.inv_dy2) * a.dcoef;
+                        R pres = (p[i * ld + j] - p[i * ld + j - 1]) * a.inv_dy;
+                        R rhs = diff - conv - pres;
+                        if (ray) rhs += s[i * ld + j];
+                        vs[i * ld + j] = vc + a.dt * rhs;
+                    }
+                }
+            }
+            __syncthreads();
+
+            // ---- Poisson right-hand side into registers (b dx^2 dy^2, rayleigh.py:428-434) ----------
+            R c[TI][TJ];
+            CELL_LOOP {
+                const int i = i0 + r, j = j0 + k;
+                c[r][k] = R(0);
+                if (CELL_OK(i, j))
+                    c[r][k] = ((us[(i + 1) * ld + j] - us[i * ld + j]) * a.inv_dx + (vs[i * ld + j + 1] - vs[i * ld + j]) * a.inv_dy) * a.cscale;
+            }
+            // ---- Jacobi sweeps, poisson(): rayleigh.py:412-456 / mixing.py:421-465 -----------------------
+            R *pin = phiA, *pout = phiB;
+            for (int e = tid; e < 2 * n; e += T) phiA[e] = R(0);   // both planes: they doubled as transport scratch
+            __syncthreads();
+            R err = R(1.0e10);
+            int itp = 0;
+            while (err > a.tol) {
+                R acc = R(0);
+                if (has_tile) {
+#pragma unroll
+                    for (int r = 0; r < TI; r++) {
+                        const int i = i0 + r;
+                        if (i <= nx) {
+                            const R *rc = pin + i * ld + j0, *rw = rc - ld, *re = rc + ld;
+                            R west = rc[-1], cen = rc[0];
+#pragma unroll
+                            for (int k = 0; k < TJ; k++) {
+                                const int j = j0 + k;
+                                if (j <= ny) {
+                                    const R east = rc[k + 1];   // "north" in the reference's (i,j) naming: j+1
+                                    R nv = ((re[k] + rw[k]) * a.dy2 + (east + west) * a.dx2 - c[r][k]) * a.inv_den;
+                                    R d = nv - cen;
+                                    R w = R(1);
+                                    if (i == 1) { w += R(1); pout[j] = nv; }
+                                    if (i == nx) { w += R(1); pout[(nx + 1) * ld + j] = nv; }
+                                    if (j == 1) { w += R(1); pout[i * ld] = nv; }
+                                    if (j == ny) { if (ray) { w += R(1); pout[i * ld + ny + 1] = nv; } }
+                                    acc += w * (d * d);
+                                    pout[i * ld + j] = nv;
+                                    west = cen; cen = east;
+                                }
+                            }
+                        }
+                    }
+                }
+                acc = warp_sum(acc);
+                R *part = s_part[itp & 1];
+                if ((tid & 31) == 0) part[tid >> 5] = acc;
+                __syncthreads();
+                err = part[0];
+#pragma unroll
+                for (int w = 1; w < T / 32; w++) err += part[w];
+                R *t = pin; pin = pout; pout = t;
+                itp += 1;
+                if (itp > a.itmax) { status |= BEACON_STATUS_POISSON_OVERFLOW; break; }
+            }
+            it_total += itp;
+            const R *phi = pin;   // final iterate (mixing: its top ghost row is still 0)
+
+            // ---- p += phi (whole array, rayleigh.py:219) and corrector (:461-464) ---------------------
+            for (int e = tid; e < n; e += T) p[e] += phi[e];
+            CELL_LOOP {
+                const int i = i0 + r, j = j0 + k;
+                if (CELL_OK(i, j)) {
+                    if (i >= 2) u[i * ld + j] = us[i * ld + j] - a.dt * (phi[i * ld + j] - phi[(i - 1) * ld + j]) * a.inv_dx;
+                    if (j >= 2) v[i * ld + j] = vs[i * ld + j] - a.dt * (phi[i * ld + j] - phi[i * ld + j - 1]) * a.inv_dy;
+                }
+            }
+            __syncthreads();
+
+            // ---- transport: rayleigh.py:469-487 / mixing.py:478-495 -------------------------------------
+            // new(i,j) = A + BW*new(i-1,j) + BS*new(i,j-1); A, BW, BS from old values only.
+            // Scratch planes (3 per pass of `rows` rows) live in the phi planes (+ the Poisson-free
+            // us plane for rayleigh).
+            {
+                const int passes = a.tr_pass, rows = (nx + passes - 1) / passes;
+                R *cA = phiA, *cW = phiA + rows * ld, *cS = phiA + 2 * rows * ld;   // [rows][ld] each, row-local index
+                const R kx = a.tcoef * a.inv_dx2, ky = a.tcoef * a.inv_dy2;
+                for (int ps = 0; ps < passes; ps++) {
+                    const int ib = 1 + ps * rows, ie = min(nx, ib + rows - 1);
+                    CELL_LOOP {
+                        const int i = i0 + r, j = j0 + k;
+                        if (CELL_OK(i, j) && i >= ib && i <= ie) {
+                            const R uE = u[(i + 1) * ld + j], uW = u[i * ld + j], vN = v[i * ld + j + 1], vS = v[i * ld + j];
+                            const R sc = s[i * ld + j], sE = s[(i + 1) * ld + j], sN = s[i * ld + j + 1];
+                            // T += dt*(diff - conv), with TW = (Tw+Tc)/2 and TS = (Ts+Tc)/2 split off
+                            R diff0 = ((sE - R(2) * sc) * a.inv_dx2 + (sN - R(2) * sc) * a.inv_dy2) * a.tcoef;
+                            R conv0 = (uE * (R(0.5) * (sE + sc)) - uW * (R(0.5) * sc)) * a.inv_dx +
+                                      (vN * (R(0.5) * (sN + sc)) - vS * (R(0.5) * sc)) * a.inv_dy;
+                            const int e = (i - ib) * ld + j;
+                            cA[e] = sc + a.dt * (diff0 - conv0);
+                            cW[e] = a.dt * (kx + R(0.5) * uW * a.inv_dx);
+                            cS[e] = a.dt * (ky + R(0.5) * vS * a.inv_dy);
+                        }
+                    }
+                    __syncthreads();
+                    if (tid < 32) {
+                        // skewed wavefront: lane l owns rows ib + l*RPL .. ; at step t it does column t - l + 1
+                        constexpr int RPL = MAC_RPL;
+                        const int lanes = (ie - ib + 1 + RPL - 1) / RPL;
+                        const int lane = tid;
+                        const int rb = ib + lane * RPL;
+                        R prev[RPL];            // new values of my rows at column j-1
+#pragma unroll
+                        for (int q = 0; q < RPL; q++) prev[q] = (rb + q <= ie) ? s[(rb + q) * ld + 0] : R(0);
+                        R last_new = R(0);      // new value of my last row at the column just done
+                        const int steps = ny + lanes - 1;
+                        for (int t = 0; t < steps; t++) {
+                            // west value for my first row: lane-1's last row at the same column
+                            R wv = __shfl_up_sync(0xffffffffu, last_new, 1);
+                            const int j = t - lane + 1;
+                            if (lane < lanes && j >= 1 && j <= ny) {
+                                if (lane == 0) wv = s[(ib - 1) * ld + j];     // row ib-1: previous pass (new) or ghost
+#pragma unroll
+                                for (int q = 0; q < RPL; q++) {
+                                    const int i = rb + q;
+                                    if (i <= ie) {
+                                        const int e = (i - ib) * ld + j;
+                                        R nv = (cA[e] + cS[e] * prev[q]) + cW[e] * wv;
+                                        s[i * ld + j] = nv;
+                                        prev[q] = nv;
+                                        wv = nv;
+                                    }
+                                }
+                                last_new = wv;
+                            }
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+        }   // sub-steps
+
+        // ---- observations (probe history) and reward --------------------------------------------------
+        {
+            R *hist = a.obs_hist + (size_t)b * a.n_obs;
+            const int per_step = 3 * a.nx_obs_pts * a.ny_obs_pts;
+            R *out = a.obs + orow * a.n_obs;
+            for (int e = tid; e < a.n_obs; e += T) {              // rayleigh.py:243-262
+                int st = e / per_step, rem = e - st * per_step;
+                R val;
+                if (st < a.n_obs_steps - 1) val = hist[e + per_step];
+                else {
+                    int f = rem / (a.nx_obs_pts * a.ny_obs_pts), q = rem - f * (a.nx_obs_pts * a.ny_obs_pts);
+                    int pi = q / a.ny_obs_pts, pj = q - pi * a.ny_obs_pts;
+                    int x = a.nx_obs / 2 + pi * a.nx_obs, y = a.ny_obs / 2 + pj * a.ny_obs;
+                    val = (f == 0) ? s[x * ld + y] : (f == 1 ? u[x * ld + y] : v[x * ld + y]);
+                }
+                out[e] = val;
+            }
+            __syncthreads();
+            for (int e = tid; e < a.n_obs; e += T) hist[e] = out[e];
+            R rwd;
+            if (ray) {                                            // rayleigh.py:265-275 (sequential sum)
+                rwd = R(0);
+                if (tid == 0) {
+                    R nu = R(0);
+                    for (int i = 1; i <= nx; i++) nu -= (s[i * ld + 1] - a.Th) / (R(0.5) * a.dy);
+                    nu /= R(nx);
+                    rwd = -nu;
+                }
+            } else {                                              // mixing.py:259-264 (mean over the whole array)
+                R part = R(0);
+                for (int e = tid; e < n; e += T) part += rabs(s[e] - a.ref_c);
+                rwd = -(block_sum(part, s_red) / R(n));
+            }
+            bool nonfinite = false;
+            for (int e = tid; e < n; e += T) nonfinite |= !finite_(s[e]) | !finite_(u[e]) | !finite_(v[e]);
+            if (__syncthreads_or(nonfinite ? 1 : 0)) status |= BEACON_STATUS_NONFINITE;
+            if (tid == 0) {
+                a.rwd[orow] = rwd;
+                bool horizon = stp == a.n_act - 1;
+                a.done[orow] = horizon; a.trunc[orow] = horizon;
+                if (a.iters) a.iters[orow] = it_total;
+            }
+            stp += 1;
+        }
+    }   // actions
+
+    if (resetting) {
+        // reset observation: history is zero, newest slot sampled from the init state
+        __syncthreads();
+        R *hist = a.obs_hist + (size_t)b * a.n_obs;
+        const int per_step = 3 * a.nx_obs_pts * a.ny_obs_pts;
+        for (int e = tid; e < a.n_obs; e += T) {
+            int st = e / per_step, rem = e - st * per_step;
+            R val = R(0);
+            if (st == a.n_obs_steps - 1) {
+                int f = rem / (a.nx_obs_pts * a.ny_obs_pts), q = rem - f * (a.nx_obs_pts * a.ny_obs_pts);
+                int pi = q / a.ny_obs_pts, pj = q - pi * a.ny_obs_pts;
+                int x = a.nx_obs / 2 + pi * a.nx_obs, y = a.ny_obs / 2 + pj * a.ny_obs;
+                val = (f == 0) ? gs[x * ld + y] : (f == 1 ? gu[x * ld + y] : gv[x * ld + y]);
+            }
+            hist[e] = val;
+            a.obs[(size_t)b * a.n_obs + e] = val;
+        }
+        return;
+    }
+
+    // ---- store state -----------------------------------------------------------------------------------
+    __syncthreads();
+    if (SMEM) {
+        for (int e = tid; e < n; e += T) { gu[e] = u[e]; gv[e] = v[e]; gp[e] = p[e]; gs[e] = s[e]; a.us[row + e] = us[e]; a.vs[row + e] = vs[e]; }
+    }
+    if (tid == 0) { a.stp[b] = stp; if (a.status) a.status[b] = status; }
+#undef CELL_LOOP
+#undef CELL_OK
+}
+
+// ---------------------------------------------------------------------------------------
+template <typename R> class MacEnv : public Env {
+    beacon_mac_params p;
+    int kind;
+    DeviceBuffer u, v, pp, s, us, vs, cc, a_cur, a_int, obs_hist, stp, u0, v0, p0, s0;
+    MacArgs<R> base{};
+    void (*kernel)(const MacArgs<R>) = nullptr;
+    int T = 0;
+    size_t smem = 0;
+
+public:
+    MacEnv(const beacon_common &c, const beacon_mac_params &pp_, int kind_, const double *hu, const double *hv,
+           const double *hp, const double *hs)
+        : p(pp_), kind(kind_)
+    {
+        common = c;
+        const int B = c.batch, nx = p.nx, ny = p.ny, ld = ny + 2, n = (nx + 2) * ld;
+        const bool ray = kind == BEACON_RAYLEIGH;
+        BEACON_REQUIRE(nx >= 4 && ny >= 4 && p.ndt_act > 0 && p.itmax > 0, "mac2d: bad sizes");
+        BEACON_REQUIRE(hs != nullptr, "mac2d: scalar init field must not be NULL");
+        if (ray) {
+            BEACON_REQUIRE(hu && hv && hp, "rayleigh: init fields must not be NULL");
+            BEACON_REQUIRE(p.n_sgts >= 1 && p.n_sgts <= 128 && p.nx_sgts >= 1 && p.n_sgts * p.nx_sgts <= nx, "rayleigh: bad segment layout");
+        }
+        const int npts = p.nx_obs_pts * p.ny_obs_pts;
+        BEACON_REQUIRE(npts > 0 && p.n_obs_steps > 0, "mac2d: bad probe layout");
+        BEACON_REQUIRE(p.nx_obs / 2 + (p.nx_obs_pts - 1) * p.nx_obs <= nx + 1 && p.ny_obs / 2 + (p.ny_obs_pts - 1) * p.ny_obs <= ny + 1,
+                       "mac2d: probes outside the domain");
+        info.kind = kind; info.batch = B; info.dtype = real_traits<R>::dtype; info.device = c.device;
+        info.n_obs = 3 * p.n_obs_steps * npts; info.act_dim = ray ? p.n_sgts : 1; info.act_is_int = ray ? 0 : 1;
+        info.rwd_dim = 1; info.n_act = p.n_act; info.noise_dim = 0;
+
+        MacArgs<R> &a = base;
+        // kernel variant: all planes in shared memory when 8 planes fit, else phi planes only
+        const size_t plane = (size_t)n * sizeof(R);
+        int TI, TJ;
+        if (8 * plane + 1024 <= 220 * 1024 && ((nx + 1) / 2) * ((ny + 4) / 5) <= 256) {
+            kernel = mac_kernel<R, 2, 5, 256, true>; T = 256; TI = 2; TJ = 5; smem = 8 * plane;
+        } else if (2 * plane + 1024 <= 220 * 1024 && ((nx + 3) / 4) * ((ny + 4) / 5) <= 512) {
+            kernel = mac_kernel<R, 4, 5, 512, false>; T = 512; TI = 4; TJ = 5; smem = 2 * plane;
+        } else
+            throw Error(BEACON_ERR_UNSUPPORTED, "mac2d: grid too large for the one-CTA-per-env kernel (max ~100x100 cells)");
+        // transport scratch = 3 planes of ceil(nx/passes) rows inside the two phi planes
+        a.tr_pass = 1;
+        while (3 * (size_t)((nx + a.tr_pass - 1) / a.tr_pass) * ld > 2 * (size_t)n || (nx + a.tr_pass - 1) / a.tr_pass > 32 * MAC_RPL)
+            a.tr_pass++;
+        BEACON_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+        const size_t nb = (size_t)B * plane;
+        u.alloc(nb); v.alloc(nb); pp.alloc(nb); s.alloc(nb); us.alloc(nb); vs.alloc(nb);
+        a_cur.alloc((size_t)B * (ray ? p.n_sgts : 1) * sizeof(R)); a_int.alloc((size_t)B * 4);
+        obs_hist.alloc((size_t)B * info.n_obs * sizeof(R)); stp.alloc((size_t)B * 4);
+        if (ray) { upload_as<R>(u0, hu, n); upload_as<R>(v0, hv, n); upload_as<R>(p0, hp, n); }
+        upload_as<R>(s0, hs, n);
+        add_field("u", u.ptr, n); add_field("v", v.ptr, n); add_field("p", pp.ptr, n); add_field(ray ? "T" : "C", s.ptr, n);
+        add_field("us", us.ptr, n); add_field("vs", vs.ptr, n);
+        if (ray) add_field("a", a_cur.ptr, p.n_sgts); else add_field("a", a_int.ptr, 1, true);
+        add_field("obs", obs_hist.ptr, info.n_obs); add_field("stp", stp.ptr, 1, true);
+
+        a.nx = nx; a.ny = ny; a.ld = ld; a.n = n; a.ndt_act = p.ndt_act; a.n_act = p.n_act; a.kind = kind;
+        a.n_sgts = p.n_sgts; a.nx_sgts = p.nx_sgts > 0 ? p.nx_sgts : 1; a.itmax = p.itmax;
+        a.tiles_i = (nx + TI - 1) / TI; a.tiles_j = (ny + TJ - 1) / TJ;
+        a.nx_obs_pts = p.nx_obs_pts; a.ny_obs_pts = p.ny_obs_pts; a.n_obs_steps = p.n_obs_steps; a.nx_obs = p.nx_obs; a.ny_obs = p.ny_obs;
+        a.n_obs = info.n_obs;
+        const double dx = p.dx, dy = p.dy, dt = p.dt;
+        a.dx = (R)dx; a.dy = (R)dy; a.dt = (R)dt; a.inv_dx = (R)(1.0 / dx); a.inv_dy = (R)(1.0 / dy);
+        a.inv_dx2 = (R)(1.0 / (dx * dx)); a.inv_dy2 = (R)(1.0 / (dy * dy)); a.dx2 = (R)(dx * dx); a.dy2 = (R)(dy * dy);
+        a.inv_den = (R)(0.5 / (dx * dx + dy * dy));
+        a.cscale = (R)(dx * dx * dy * dy / dt);                   // b*dx*dx*dy*dy with b = div/dt
+        a.dcoef = (R)(ray ? std::sqrt(p.pr / p.ra) : 1.0 / p.re); // momentum diffusion factor
+        a.tcoef = (R)(ray ? 1.0 / std::sqrt(p.pr * p.ra) : 1.0 / p.pe);
+        a.Tc = (R)p.Tc; a.Th = (R)p.Th; a.Cmax = (R)p.C; a.u_max = (R)p.u_max; a.ref_c = (R)p.ref_c; a.tol = (R)p.tol;
+        a.B = B;
+        a.u = u.as<R>(); a.v = v.as<R>(); a.p = pp.as<R>(); a.s = s.as<R>(); a.us = us.as<R>(); a.vs = vs.as<R>();
+        a.a_cur = a_cur.as<R>(); a.a_int = a_int.as<int32_t>(); a.obs_hist = obs_hist.as<R>(); a.stp = stp.as<int32_t>();
+        a.u0 = u0.as<R>(); a.v0 = v0.as<R>(); a.p0 = p0.as<R>(); a.s0 = s0.as<R>();
+    }
+    void run(const MacArgs<R> &a, cudaStream_t st)
+    {
+        kernel<<<a.B, T, smem, st>>>(a);
+        BEACON_CUDA_CHECK(cudaGetLastError());
+        launches++;
+    }
+    void reset(const ResetArgs &r) override
+    {
+        BEACON_REQUIRE(r.obs != nullptr, "reset: obs must not be NULL");
+        MacArgs<R> a = base; a.mode = 1; a.mask = r.mask; a.obs = (R *)r.obs;
+        run(a, r.stream);
+    }
+    void step(const StepArgs &s_) override
+    {
+        MacArgs<R> a = base; a.mode = 0; a.n_fused = s_.n_fused; a.actions = s_.actions;
+        a.obs = (R *)s_.obs; a.rwd = (R *)s_.rwd; a.done = s_.done; a.trunc = s_.trunc; a.status = s_.status; a.iters = s_.iters;
+        run(a, s_.stream);
+    }
+};
+
+Env *make_mac(const beacon_common &c, const beacon_mac_params &p, int kind, const double *u0, const double *v0,
+              const double *p0, const double *s0)
+{
+    if (c.dtype == BEACON_F64) return new MacEnv<double>(c, p, kind, u0, v0, p0, s0);
+    if (c.dtype == BEACON_F32) return new MacEnv<float>(c, p, kind, u0, v0, p0, s0);
+    throw Error(BEACON_ERR_INVALID, "unknown dtype");
+}
+
+}  // namespace beacon
