@@ -25,6 +25,8 @@
 //   * rayleigh (50x50): all eight planes live in shared memory (173 KB fp64); mixing (100x100,
 //     83 KB per plane): phi planes in shared memory, the other planes stay in L2-resident global
 //     memory (Poisson dominates: ~21 k sweeps per action vs 250 predictor/transport passes).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace beacon {
@@ -424,6 +426,340 @@ __global__ void __launch_bounds__(T) mac_kernel(const MacArgs<R> a)
 }
 
 // ---------------------------------------------------------------------------------------
+// Register-resident variant (rayleigh-sized grids: five planes fit twice per SM).
+//   * shared memory: U, V, S planes + two phi exchange planes (5 x 21.6 KB fp64) -> 2 CTAs/SM;
+//   * each thread keeps phi AND the Poisson right-hand side of its TI x TJ tile in registers for
+//     the whole solve; a sweep reads only the 2(TI+TJ) halo values from the exchange plane,
+//     writes its tile (and the ghost copies it owns) to the other plane: one __syncthreads;
+//   * predictor output (us, vs) is staged in registers over one barrier and then overwrites U, V
+//     in place (old u, v are dead after the predictor; wall entries are 0 in both), the corrector
+//     is then a pointwise in-place update; p stays in L2-resident global memory;
+//   * the first sweep (phi = 0) needs no halo: the exchange planes are never zeroed.
+// ---------------------------------------------------------------------------------------
+template <typename R, int TI, int TJ, int T>
+__global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ R s_part[2][T / 32];
+    __shared__ R s_seg[128];
+    __shared__ R s_act[128];
+    const int tid = threadIdx.x, b = blockIdx.x;
+    const int nx = a.nx, ny = a.ny, ld = a.ld, n = a.n;
+    const bool resetting = a.mode == 1;
+    if (resetting && a.mask && !a.mask[b]) return;
+
+    R *PA = reinterpret_cast<R *>(smem_raw), *PB = PA + n, *U = PB + n, *V = U + n, *S = V + n;
+    const size_t row = (size_t)b * n;
+    R *gu = a.u + row, *gv = a.v + row, *gp = a.p + row, *gs = a.s + row;
+
+    const bool has_tile = tid < a.tiles_i * a.tiles_j;
+    const int ti = tid / a.tiles_j, tj = tid - ti * a.tiles_j;
+    const int i0 = 1 + ti * TI, j0 = 1 + tj * TJ;
+    const bool top = has_tile && i0 == 1, bot = has_tile && i0 + TI - 1 == nx;
+    const bool lef = has_tile && j0 == 1, rig = has_tile && j0 + TJ - 1 == ny;
+#define TILE_LOOP                                      \
+    _Pragma("unroll") for (int r = 0; r < TI; r++)     \
+    _Pragma("unroll") for (int k = 0; k < TJ; k++)
+
+    if (resetting) {                                   // rayleigh.py:89-128
+        for (int e = tid; e < n; e += T) { gu[e] = a.u0[e]; gv[e] = a.v0[e]; gp[e] = a.p0[e]; gs[e] = a.s0[e]; }
+        for (int e = tid; e < a.n_sgts; e += T) a.a_cur[(size_t)b * a.n_sgts + e] = R(0);
+        const int per_step = 3 * a.nx_obs_pts * a.ny_obs_pts;
+        R *hist = a.obs_hist + (size_t)b * a.n_obs;
+        for (int e = tid; e < a.n_obs; e += T) {
+            int st = e / per_step, rem = e - st * per_step;
+            R val = R(0);
+            if (st == a.n_obs_steps - 1) {
+                int f = rem / (a.nx_obs_pts * a.ny_obs_pts), q = rem - f * (a.nx_obs_pts * a.ny_obs_pts);
+                int pi = q / a.ny_obs_pts, pj = q - pi * a.ny_obs_pts;
+                int x = a.nx_obs / 2 + pi * a.nx_obs, y = a.ny_obs / 2 + pj * a.ny_obs;
+                val = (f == 0) ? a.s0[x * ld + y] : (f == 1 ? a.u0[x * ld + y] : a.v0[x * ld + y]);
+            }
+            hist[e] = val;
+            a.obs[(size_t)b * a.n_obs + e] = val;
+        }
+        if (tid == 0) a.stp[b] = 0;
+        return;
+    }
+    for (int e = tid; e < n; e += T) { U[e] = gu[e]; V[e] = gv[e]; S[e] = gs[e]; }
+    int stp = a.stp[b];
+    int status = 0;
+
+    for (int act = 0; act < a.n_fused; act++) {
+        const size_t orow = (size_t)act * a.B + b;
+        __syncthreads();
+        if (tid == 0) {                                            // rayleigh.py:164-171
+            const R *ain = (const R *)a.actions + orow * a.n_sgts;
+            const int ns = a.n_sgts;
+            for (int j = 0; j < ns; j++) s_act[j] = ain[j];
+            R mean = np_pairwise_small(s_act, ns) / R(ns);
+            R m = R(1);
+            for (int j = 0; j < ns; j++) { s_act[j] = s_act[j] - mean; m = np_max(m, rabs(s_act[j]) / a.Cmax); }
+            for (int j = 0; j < ns; j++) { s_act[j] = s_act[j] / m; s_seg[j] = a.Th + s_act[j]; a.a_cur[(size_t)b * ns + j] = s_act[j]; }
+        }
+        __syncthreads();
+        long long it_total = 0;
+
+        for (int it = 0; it < a.ndt_act; it++) {
+            // ---- boundary conditions, rayleigh.py:180-202 ------------------------------------------
+            for (int k = tid; k < 2 * (nx + 2) + 2 * (ny + 2); k += T) {
+                if (k < ny + 2) {
+                    int j = k;
+                    if (j >= 1 && j <= ny) { U[1 * ld + j] = R(0); S[0 * ld + j] = S[1 * ld + j]; }
+                    if (j >= 2 && j <= ny) V[0 * ld + j] = -V[1 * ld + j];
+                } else if (k < 2 * (ny + 2)) {
+                    int j = k - (ny + 2);
+                    if (j >= 1 && j <= ny) { U[(nx + 1) * ld + j] = R(0); S[(nx + 1) * ld + j] = S[nx * ld + j]; }
+                    if (j >= 2 && j <= ny) V[(nx + 1) * ld + j] = -V[nx * ld + j];
+                } else if (k < 2 * (ny + 2) + (nx + 2)) {
+                    int i = k - 2 * (ny + 2);
+                    if (i >= 1 && i <= nx + 1) U[i * ld + ny + 1] = (i == 1 || i == nx + 1) ? -R(0) : -U[i * ld + ny];
+                    if (i >= 1 && i <= nx) { V[i * ld + ny + 1] = R(0); S[i * ld + ny + 1] = R(2) * a.Tc - S[i * ld + ny]; }
+                } else {
+                    int i = k - 2 * (ny + 2) - (nx + 2);
+                    if (i >= 1 && i <= nx + 1) U[i * ld + 0] = (i == 1 || i == nx + 1) ? -R(0) : -U[i * ld + 1];
+                    if (i >= 1 && i <= nx) {
+                        V[i * ld + 1] = R(0);
+                        int sg = (i - 1) / a.nx_sgts;
+                        if (sg < a.n_sgts) S[i * ld + 0] = R(2) * s_seg[sg] - S[i * ld + 1];
+                    }
+                }
+            }
+            __syncthreads();
+
+            // ---- predictor into registers, rayleigh.py:371-407 -----------------------------------------
+            R us[TI][TJ], vs[TI][TJ];
+            if (has_tile) {
+                TILE_LOOP {
+                    const int i = i0 + r, j = j0 + k, e = i * ld + j;
+                    const R uc = U[e], vc = V[e], pc = gp[e];
+                    us[r][k] = uc; vs[r][k] = vc;
+                    if (i >= 2) {
+                        R uE = R(0.5) * (U[e + ld] + uc), uW = R(0.5) * (uc + U[e - ld]);
+                        R uN = R(0.5) * (U[e + 1] + uc), uS = R(0.5) * (uc + U[e - 1]);
+                        R vN = R(0.5) * (V[e + 1] + V[e - ld + 1]), vS = R(0.5) * (vc + V[e - ld]);
+                        R conv = (uE * uE - uW * uW) * a.inv_dx + (uN * vN - uS * vS) * a.inv_dy;
+                        R diff = ((U[e + ld] - R(2) * uc + U[e - ld]) * a.inv_dx2 + (U[e + 1] - R(2) * uc + U[e - 1]) * a.inv_dy2) * a.dcoef;
+                        R pres = (pc - gp[e - ld]) * a.inv_dx;
+                        us[r][k] = uc + a.dt * (diff - conv - pres);
+                    }
+                    if (j >= 2) {
+                        R vE = R(0.5) * (V[e + ld] + vc), vW = R(0.5) * (vc + V[e - ld]);
+                        R uE = R(0.5) * (U[e + ld] + U[e + ld - 1]), uW = R(0.5) * (uc + U[e - 1]);
+                        R vN = R(0.5) * (V[e + 1] + vc), vS = R(0.5) * (vc + V[e - 1]);
+                        R conv = (uE * vE - uW * vW) * a.inv_dx + (vN * vN - vS * vS) * a.inv_dy;
+                        R diff = ((V[e + ld] - R(2) * vc + V[e - ld]) * a.inv_dx2 + (V[e + 1] - R(2) * vc + V[e - 1]) * a.inv_dy2) * a.dcoef;
+                        R pres = (pc - gp[e - 1]) * a.inv_dy;
+                        vs[r][k] = vc + a.dt * (diff - conv - pres + S[e]);
+                    }
+                }
+            }
+            __syncthreads();                       // every read of the old u, v is done
+            if (has_tile) { TILE_LOOP { const int e = (i0 + r) * ld + j0 + k; U[e] = us[r][k]; V[e] = vs[r][k]; } }
+            __syncthreads();                       // U, V now hold the starred fields (walls: 0)
+
+            // ---- Poisson: rhs and phi in registers, rayleigh.py:412-456 -------------------------------
+            R c[TI][TJ], phi[TI][TJ];
+            if (has_tile) {
+                TILE_LOOP {
+                    const int e = (i0 + r) * ld + j0 + k;
+                    const R ue = (r < TI - 1) ? us[r + 1][k] : U[e + ld];
+                    const R vn = (k < TJ - 1) ? vs[r][k + 1] : V[e + 1];
+                    c[r][k] = ((ue - us[r][k]) * a.inv_dx + (vn - vs[r][k]) * a.inv_dy) * a.cscale;
+                    phi[r][k] = R(0);
+                }
+            }
+            R *pin = PA, *pout = PB;
+            R err = R(1.0e10);
+            int itp = 0;
+            while (err > a.tol) {
+                R acc = R(0);
+                if (has_tile) {
+                    R hn[TJ], hs[TJ], hw[TI], he[TI];    // halo: rows i0-1 / i0+TI, columns j0-1 / j0+TJ
+                    if (itp > 0) {
+#pragma unroll
+                        for (int k = 0; k < TJ; k++) { hn[k] = pin[(i0 - 1) * ld + j0 + k]; hs[k] = pin[(i0 + TI) * ld + j0 + k]; }
+#pragma unroll
+                        for (int r = 0; r < TI; r++) { hw[r] = pin[(i0 + r) * ld + j0 - 1]; he[r] = pin[(i0 + r) * ld + j0 + TJ]; }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < TJ; k++) { hn[k] = R(0); hs[k] = R(0); }
+#pragma unroll
+                        for (int r = 0; r < TI; r++) { hw[r] = R(0); he[r] = R(0); }
+                    }
+                    R nw[TI][TJ];
+                    TILE_LOOP {
+                        const R xm = (r > 0) ? phi[r - 1][k] : hn[k], xp = (r < TI - 1) ? phi[r + 1][k] : hs[k];
+                        const R ym = (k > 0) ? phi[r][k - 1] : hw[r], yp = (k < TJ - 1) ? phi[r][k + 1] : he[r];
+                        const R v = ((xp + xm) * a.dy2 + (yp + ym) * a.dx2 - c[r][k]) * a.inv_den;
+                        const R d = v - phi[r][k];
+                        R w = d * d;
+                        acc += w;
+                        if (r == 0 && top) acc += w;                 // ghost copies re-count wall cells
+                        if (r == TI - 1 && bot) acc += w;
+                        if (k == 0 && lef) acc += w;
+                        if (k == TJ - 1 && rig) acc += w;
+                        nw[r][k] = v;
+                    }
+                    TILE_LOOP { phi[r][k] = nw[r][k]; pout[(i0 + r) * ld + j0 + k] = nw[r][k]; }
+                    if (top) {
+#pragma unroll
+                        for (int k = 0; k < TJ; k++) pout[j0 + k] = nw[0][k];
+                    }
+                    if (bot) {
+#pragma unroll
+                        for (int k = 0; k < TJ; k++) pout[(nx + 1) * ld + j0 + k] = nw[TI - 1][k];
+                    }
+                    if (lef) {
+#pragma unroll
+                        for (int r = 0; r < TI; r++) pout[(i0 + r) * ld] = nw[r][0];
+                    }
+                    if (rig) {
+#pragma unroll
+                        for (int r = 0; r < TI; r++) pout[(i0 + r) * ld + ny + 1] = nw[r][TJ - 1];
+                    }
+                }
+                acc = warp_sum(acc);
+                R *part = s_part[itp & 1];
+                if ((tid & 31) == 0) part[tid >> 5] = acc;
+                __syncthreads();
+                err = part[0];
+#pragma unroll
+                for (int w = 1; w < T / 32; w++) err += part[w];
+                R *t = pin; pin = pout; pout = t;
+                itp += 1;
+                if (itp > a.itmax) { status |= BEACON_STATUS_POISSON_OVERFLOW; break; }
+            }
+            it_total += itp;
+
+            // ---- p += phi (ghosts included, rayleigh.py:219) and in-place corrector (:461-464) ----------
+            if (has_tile) {
+                TILE_LOOP {
+                    const int i = i0 + r, j = j0 + k, e = i * ld + j;
+                    gp[e] += phi[r][k];
+                    if (i >= 2) { const R pw = (r > 0) ? phi[r - 1][k] : pin[e - ld]; U[e] = U[e] - a.dt * (phi[r][k] - pw) * a.inv_dx; }
+                    if (j >= 2) { const R ps = (k > 0) ? phi[r][k - 1] : pin[e - 1]; V[e] = V[e] - a.dt * (phi[r][k] - ps) * a.inv_dy; }
+                }
+                if (top) {
+#pragma unroll
+                    for (int k = 0; k < TJ; k++) gp[j0 + k] += phi[0][k];
+                }
+                if (bot) {
+#pragma unroll
+                    for (int k = 0; k < TJ; k++) gp[(nx + 1) * ld + j0 + k] += phi[TI - 1][k];
+                }
+                if (lef) {
+#pragma unroll
+                    for (int r = 0; r < TI; r++) gp[(i0 + r) * ld] += phi[r][0];
+                }
+                if (rig) {
+#pragma unroll
+                    for (int r = 0; r < TI; r++) gp[(i0 + r) * ld + ny + 1] += phi[r][TJ - 1];
+                }
+            }
+            __syncthreads();
+
+            // ---- transport, rayleigh.py:469-487 (see mac_kernel for the recurrence) -------------------
+            {
+                const int passes = a.tr_pass, rows = (nx + passes - 1) / passes;
+                R *cA = PA, *cW = PA + rows * ld, *cS = PA + 2 * rows * ld;
+                const R kx = a.tcoef * a.inv_dx2, ky = a.tcoef * a.inv_dy2;
+                for (int ps = 0; ps < passes; ps++) {
+                    const int ib = 1 + ps * rows, ie = min(nx, ib + rows - 1);
+                    if (has_tile) {
+                        TILE_LOOP {
+                            const int i = i0 + r, j = j0 + k;
+                            if (i >= ib && i <= ie) {
+                                const int e0 = i * ld + j;
+                                const R uE = U[e0 + ld], uW = U[e0], vN = V[e0 + 1], vS = V[e0];
+                                const R sc = S[e0], sE = S[e0 + ld], sN = S[e0 + 1];
+                                R diff0 = ((sE - R(2) * sc) * a.inv_dx2 + (sN - R(2) * sc) * a.inv_dy2) * a.tcoef;
+                                R conv0 = (uE * (R(0.5) * (sE + sc)) - uW * (R(0.5) * sc)) * a.inv_dx +
+                                          (vN * (R(0.5) * (sN + sc)) - vS * (R(0.5) * sc)) * a.inv_dy;
+                                const int e = (i - ib) * ld + j;
+                                cA[e] = sc + a.dt * (diff0 - conv0);
+                                cW[e] = a.dt * (kx + R(0.5) * uW * a.inv_dx);
+                                cS[e] = a.dt * (ky + R(0.5) * vS * a.inv_dy);
+                            }
+                        }
+                    }
+                    __syncthreads();
+                    if (tid < 32) {
+                        constexpr int RPL = MAC_RPL;
+                        const int lanes = (ie - ib + 1 + RPL - 1) / RPL;
+                        const int lane = tid, rb = ib + lane * RPL;
+                        R prev[RPL];
+#pragma unroll
+                        for (int q = 0; q < RPL; q++) prev[q] = (rb + q <= ie) ? S[(rb + q) * ld + 0] : R(0);
+                        R last_new = R(0);
+                        const int steps = ny + lanes - 1;
+                        for (int t = 0; t < steps; t++) {
+                            R wv = __shfl_up_sync(0xffffffffu, last_new, 1);
+                            const int j = t - lane + 1;
+                            if (lane < lanes && j >= 1 && j <= ny) {
+                                if (lane == 0) wv = S[(ib - 1) * ld + j];
+#pragma unroll
+                                for (int q = 0; q < RPL; q++) {
+                                    const int i = rb + q;
+                                    if (i <= ie) {
+                                        const int e = (i - ib) * ld + j;
+                                        R nv = (cA[e] + cS[e] * prev[q]) + cW[e] * wv;
+                                        S[i * ld + j] = nv;
+                                        prev[q] = nv;
+                                        wv = nv;
+                                    }
+                                }
+                                last_new = wv;
+                            }
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+        }   // sub-steps
+
+        // ---- observations and reward, rayleigh.py:243-275 ---------------------------------------------
+        {
+            R *hist = a.obs_hist + (size_t)b * a.n_obs;
+            const int per_step = 3 * a.nx_obs_pts * a.ny_obs_pts;
+            R *out = a.obs + orow * a.n_obs;
+            for (int e = tid; e < a.n_obs; e += T) {
+                int st = e / per_step, rem = e - st * per_step;
+                R val;
+                if (st < a.n_obs_steps - 1) val = hist[e + per_step];
+                else {
+                    int f = rem / (a.nx_obs_pts * a.ny_obs_pts), q = rem - f * (a.nx_obs_pts * a.ny_obs_pts);
+                    int pi = q / a.ny_obs_pts, pj = q - pi * a.ny_obs_pts;
+                    int x = a.nx_obs / 2 + pi * a.nx_obs, y = a.ny_obs / 2 + pj * a.ny_obs;
+                    val = (f == 0) ? S[x * ld + y] : (f == 1 ? U[x * ld + y] : V[x * ld + y]);
+                }
+                out[e] = val;
+            }
+            __syncthreads();
+            for (int e = tid; e < a.n_obs; e += T) hist[e] = out[e];
+            bool nonfinite = false;
+            for (int e = tid; e < n; e += T) nonfinite |= !finite_(S[e]) | !finite_(U[e]) | !finite_(V[e]);
+            if (__syncthreads_or(nonfinite ? 1 : 0)) status |= BEACON_STATUS_NONFINITE;
+            if (tid == 0) {
+                R nu = R(0);
+                for (int i = 1; i <= nx; i++) nu -= (S[i * ld + 1] - a.Th) / (R(0.5) * a.dy);
+                nu /= R(nx);
+                a.rwd[orow] = -nu;
+                bool horizon = stp == a.n_act - 1;
+                a.done[orow] = horizon; a.trunc[orow] = horizon;
+                if (a.iters) a.iters[orow] = it_total;
+            }
+            stp += 1;
+        }
+    }   // actions
+
+    __syncthreads();
+    for (int e = tid; e < n; e += T) { gu[e] = U[e]; gv[e] = V[e]; gs[e] = S[e]; }
+    if (tid == 0) { a.stp[b] = stp; if (a.status) a.status[b] = status; }
+#undef TILE_LOOP
+}
+
+// ---------------------------------------------------------------------------------------
 template <typename R> class MacEnv : public Env {
     beacon_mac_params p;
     int kind;
@@ -432,6 +768,7 @@ template <typename R> class MacEnv : public Env {
     void (*kernel)(const MacArgs<R>) = nullptr;
     int T = 0;
     size_t smem = 0;
+    bool reg_variant = false;
 
 public:
     MacEnv(const beacon_common &c, const beacon_mac_params &pp_, int kind_, const double *hu, const double *hv,
@@ -459,8 +796,10 @@ public:
         // kernel variant: all planes in shared memory when 8 planes fit, else phi planes only
         const size_t plane = (size_t)n * sizeof(R);
         int TI, TJ;
-        if (8 * plane + 1024 <= 220 * 1024 && ((nx + 1) / 2) * ((ny + 4) / 5) <= 256) {
-            kernel = mac_kernel<R, 2, 5, 256, true>; T = 256; TI = 2; TJ = 5; smem = 8 * plane;
+        reg_variant = false;
+        if (ray && nx % 2 == 0 && ny % 5 == 0 && (nx / 2) * (ny / 5) <= 256 && 5 * plane + 2048 <= 112 * 1024 && !getenv("BEACON_MAC_V1")) {
+            // five planes fit twice per SM: register-resident phi tiles, 2 CTAs/SM
+            kernel = mac_reg_kernel<R, 2, 5, 256>; T = 256; TI = 2; TJ = 5; smem = 5 * plane; reg_variant = true;
         } else if (2 * plane + 1024 <= 220 * 1024 && ((nx + 3) / 4) * ((ny + 4) / 5) <= 512) {
             kernel = mac_kernel<R, 4, 5, 512, false>; T = 512; TI = 4; TJ = 5; smem = 2 * plane;
         } else
@@ -478,7 +817,7 @@ public:
         if (ray) { upload_as<R>(u0, hu, n); upload_as<R>(v0, hv, n); upload_as<R>(p0, hp, n); }
         upload_as<R>(s0, hs, n);
         add_field("u", u.ptr, n); add_field("v", v.ptr, n); add_field("p", pp.ptr, n); add_field(ray ? "T" : "C", s.ptr, n);
-        add_field("us", us.ptr, n); add_field("vs", vs.ptr, n);
+        if (!reg_variant) { add_field("us", us.ptr, n); add_field("vs", vs.ptr, n); }
         if (ray) add_field("a", a_cur.ptr, p.n_sgts); else add_field("a", a_int.ptr, 1, true);
         add_field("obs", obs_hist.ptr, info.n_obs); add_field("stp", stp.ptr, 1, true);
 

@@ -20,6 +20,7 @@
 // bound by the fp64 pipe (4 true divisions per point per sub-step), see DESIGN.md.
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -79,6 +80,8 @@ __global__ void __launch_bounds__(T, MINB) shkadov_kernel(const ShkArgs<R> a)
     const int a0 = tid * C - a.off;                     // first point of my chunk
     const bool has_jet = (a0 + C - 1 >= a.jz0) && (a0 < a.jz0 + a.jz_len) && nj > 0;
     const int tl = tid > 0 ? tid - 1 : 0, tr = tid < T - 1 ? tid + 1 : T - 1;
+    const bool interior_thread = a0 >= 2 && a0 + C - 1 <= nx - 4;   // full stencil, all points updated
+    const bool edge_thread = (a0 <= 0) || (a0 <= nx - 1 && a0 + C - 1 >= nx - 1);   // owns point 0 or nx-1
 
     // jet zone tables (shkadov.py:224-232): weight v = (k-s)(e-k)/(0.25 (e-s)^2)
     for (int k = tid; k < a.jz_len; k += T) {
@@ -142,11 +145,13 @@ __global__ void __launch_bounds__(T, MINB) shkadov_kernel(const ShkArgs<R> a)
             const int buf = it & 1;
             R *X = ex + buf * XN * T;
             // ---- boundary conditions, shkadov.py:204-207 -------------------------------
+            if (edge_thread) {
 #pragma unroll
-            for (int m = 0; m < C; m++) {
-                int i = a0 + m;
-                if (i == 0) { hv[m] = R(1) + s_noise[it]; qv[m] = R(1); }
-                if (m > 0 && i == nx - 1) { hv[m] = hv[m - 1]; qv[m] = qv[m - 1]; }   // off guarantees m > 0
+                for (int m = 0; m < C; m++) {
+                    int i = a0 + m;
+                    if (i == 0) { hv[m] = R(1) + s_noise[it]; qv[m] = R(1); }
+                    if (m > 0 && i == nx - 1) { hv[m] = hv[m - 1]; qv[m] = qv[m - 1]; }   // off guarantees m > 0
+                }
             }
             // ---- q2h = q*q/(h+eps), shkadov.py:213 --------------------------------------
             R zv[C];
@@ -165,72 +170,82 @@ __global__ void __launch_bounds__(T, MINB) shkadov_kernel(const ShkArgs<R> a)
             }
             __syncthreads();
 
-            // ---- extended stencils -------------------------------------------------------
-            R uh[C + 5];   // h at a0-2 .. a0+C+2
-            uh[0] = X[XHL2 * T + tl]; uh[1] = X[XHL1 * T + tl];
+            // The update of a chunk.  INTERIOR chunks (every point has the full stencil and is
+            // updated: no inlet/outlet point, no phi[0]=0 face, no one-sided closure) skip all
+            // per-point index tests; the few edge threads take the general path.
+            auto update = [&](auto interior_tag) {
+                constexpr bool INTERIOR = decltype(interior_tag)::value;
+                // ---- extended stencils ---------------------------------------------------
+                R uh[C + 5];   // h at a0-2 .. a0+C+2
+                uh[0] = X[XHL2 * T + tl]; uh[1] = X[XHL1 * T + tl];
 #pragma unroll
-            for (int m = 0; m < C; m++) uh[m + 2] = hv[m];
-            uh[C + 2] = X[XH0 * T + tr]; uh[C + 3] = X[XH1 * T + tr]; uh[C + 4] = X[XH2 * T + tr];
-            R uq[C + 3], uz[C + 3];   // q, q2h at a0-2 .. a0+C
-            uq[0] = X[XQL2 * T + tl]; uq[1] = X[XQL1 * T + tl];
-            uz[0] = X[XZL2 * T + tl]; uz[1] = X[XZL1 * T + tl];
+                for (int m = 0; m < C; m++) uh[m + 2] = hv[m];
+                uh[C + 2] = X[XH0 * T + tr]; uh[C + 3] = X[XH1 * T + tr]; uh[C + 4] = X[XH2 * T + tr];
+                R uq[C + 3], uz[C + 3];   // q, q2h at a0-2 .. a0+C
+                uq[0] = X[XQL2 * T + tl]; uq[1] = X[XQL1 * T + tl];
+                uz[0] = X[XZL2 * T + tl]; uz[1] = X[XZL1 * T + tl];
 #pragma unroll
-            for (int m = 0; m < C; m++) { uq[m + 2] = qv[m]; uz[m + 2] = zv[m]; }
-            uq[C + 2] = X[XQ0 * T + tr]; uz[C + 2] = X[XZ0 * T + tr];
+                for (int m = 0; m < C; m++) { uq[m + 2] = qv[m]; uz[m + 2] = zv[m]; }
+                uq[C + 2] = X[XQ0 * T + tr]; uz[C + 2] = X[XZ0 * T + tr];
 
-            // ---- TVD faces (d1tvd, shkadov.py:494-504): F_f = u_f + 0.5 phi_f (u_{f+1}-u_f) ----
-            R Fq[C + 1], Fz[C + 1];   // faces a0-1 .. a0+C-1
-            {
-                R dq[C + 2], dz[C + 2];   // differences u_{k+1}-u_k for k = a0-2 .. a0+C-1
+                // ---- TVD faces (d1tvd, shkadov.py:494-504): F_f = u_f + 0.5 phi_f (u_{f+1}-u_f) ----
+                R Fq[C + 1], Fz[C + 1];   // faces a0-1 .. a0+C-1
+                {
+                    R dq[C + 2], dz[C + 2];   // differences u_{k+1}-u_k for k = a0-2 .. a0+C-1
 #pragma unroll
-                for (int k = 0; k < C + 2; k++) { dq[k] = uq[k + 1] - uq[k]; dz[k] = uz[k + 1] - uz[k]; }
+                    for (int k = 0; k < C + 2; k++) { dq[k] = uq[k + 1] - uq[k]; dz[k] = uz[k + 1] - uz[k]; }
 #pragma unroll
-                for (int m = 0; m < C + 1; m++) {
-                    int f = a0 - 1 + m;
-                    R rqv = dq[m] / (dq[m + 1] + R(1.0e-8));
-                    R rzv = dz[m] / (dz[m + 1] + R(1.0e-8));
-                    R pq = np_max(R(0), np_min(rqv, R(1)));
-                    R pz = np_max(R(0), np_min(rzv, R(1)));
-                    if (f <= 0) { pq = R(0); pz = R(0); }          // phi[0] = 0
-                    Fq[m] = uq[m + 1] + (R(0.5) * pq) * dq[m + 1];
-                    Fz[m] = uz[m + 1] + (R(0.5) * pz) * dz[m + 1];
+                    for (int m = 0; m < C + 1; m++) {
+                        R rqv = dq[m] / (dq[m + 1] + R(1.0e-8));
+                        R rzv = dz[m] / (dz[m + 1] + R(1.0e-8));
+                        // minmod max(0, min(r, 1)); a NaN ratio stays NaN like np.maximum/np.minimum
+                        R pq = rqv < R(0) ? R(0) : (rqv > R(1) ? R(1) : rqv);
+                        R pz = rzv < R(0) ? R(0) : (rzv > R(1) ? R(1) : rzv);
+                        if (!INTERIOR) { if (a0 - 1 + m <= 0) { pq = R(0); pz = R(0); } }   // phi[0] = 0
+                        Fq[m] = uq[m + 1] + (R(0.5) * pq) * dq[m + 1];
+                        Fz[m] = uz[m + 1] + (R(0.5) * pz) * dz[m + 1];
+                    }
                 }
-            }
-            // ---- rhs, jets, Adams-Bashforth --------------------------------------------
-            const R *sj = s_jet + buf * nj;
+                // ---- rhs, jets, Adams-Bashforth ----------------------------------------
+                const R *sj = s_jet + buf * nj;
 #pragma unroll
-            for (int m = 0; m < C; m++) {
-                const int i = a0 + m;
-                R nrh = (Fq[m + 1] - Fq[m]) * a.inv_dx;                       // rhsh = d1tvd(q)
-                R dq2h = (Fz[m + 1] - Fz[m]) * a.inv_dx;
-                // d3o2u, shkadov.py:485-491 (uh[m+2] is h_i)
-                R d3 = (-uh[m + 5] + R(6) * uh[m + 4] - R(12) * uh[m + 3] + R(10) * uh[m + 2] - R(3) * uh[m + 1]) * a.inv_2dx3;
-                if (i == nx - 3) d3 = (uh[m + 4] - R(3) * uh[m + 3] + R(3) * uh[m + 2] - uh[m + 1]) * a.inv_dx3;
-                if (i == nx - 2) d3 = (-uh[m] + R(3) * uh[m + 1] - R(3) * uh[m + 2] + uh[m + 3]) * a.inv_dx3;
-                const R hh = hv[m];
-                R nrq = R(1.2) * dq2h - a.p5d * (hh * (d3 + R(1)) - qv[m] / (hh * hh + a.eps));   // rhsq(), :507-512
-                if (has_jet) {
-                    int k = i - a.jz0;
-                    if (k >= 0 && k < a.jz_len) {
-                        if (!a.jets_overlap) {
-                            int jj = s_jj[k];
-                            if (jj >= 0) nrq += sj[jj] * s_jw[k];
-                        } else {                                             // generic: jets may overlap
-                            for (int j = 0; j < nj; j++) {
-                                int s = a.jz0 + j * a.jet_space, e = s + 2 * a.jet_hw;
-                                if (i >= s && i <= e)
-                                    nrq += sj[j] * (R((long long)(i - s) * (long long)(e - i)) / (R(0.25) * R((long long)(e - s) * (long long)(e - s))));
+                for (int m = 0; m < C; m++) {
+                    const int i = a0 + m;
+                    R nrh = (Fq[m + 1] - Fq[m]) * a.inv_dx;                       // rhsh = d1tvd(q)
+                    R dq2h = (Fz[m + 1] - Fz[m]) * a.inv_dx;
+                    // d3o2u, shkadov.py:485-491 (uh[m+2] is h_i)
+                    R d3 = (-uh[m + 5] + R(6) * uh[m + 4] - R(12) * uh[m + 3] + R(10) * uh[m + 2] - R(3) * uh[m + 1]) * a.inv_2dx3;
+                    if (!INTERIOR) {
+                        if (i == nx - 3) d3 = (uh[m + 4] - R(3) * uh[m + 3] + R(3) * uh[m + 2] - uh[m + 1]) * a.inv_dx3;
+                        if (i == nx - 2) d3 = (-uh[m] + R(3) * uh[m + 1] - R(3) * uh[m + 2] + uh[m + 3]) * a.inv_dx3;
+                    }
+                    const R hh = hv[m];
+                    R nrq = R(1.2) * dq2h - a.p5d * (hh * (d3 + R(1)) - qv[m] / (hh * hh + a.eps));   // rhsq(), :507-512
+                    if (has_jet) {
+                        int k = i - a.jz0;
+                        if (k >= 0 && k < a.jz_len) {
+                            if (!a.jets_overlap) {
+                                int jj = s_jj[k];
+                                if (jj >= 0) nrq += sj[jj] * s_jw[k];
+                            } else {                                             // generic: jets may overlap
+                                for (int j = 0; j < nj; j++) {
+                                    int s = a.jz0 + j * a.jet_space, e = s + 2 * a.jet_hw;
+                                    if (i >= s && i <= e)
+                                        nrq += sj[j] * (R((long long)(i - s) * (long long)(e - i)) / (R(0.25) * R((long long)(e - s) * (long long)(e - s))));
+                                }
                             }
                         }
                     }
+                    if (INTERIOR || (i >= 1 && i <= nx - 2)) {                    // adams(), :515-518
+                        hv[m] = hh + a.hdt * (R(-3) * nrh + rh[m]);
+                        qv[m] = qv[m] + a.hdt * (R(-3) * nrq + rq[m]);
+                        rh[m] = nrh;
+                        rq[m] = nrq;
+                    }
                 }
-                if (i >= 1 && i <= nx - 2) {                                  // adams(), :515-518
-                    hv[m] = hh + a.hdt * (R(-3) * nrh + rh[m]);
-                    qv[m] = qv[m] + a.hdt * (R(-3) * nrq + rq[m]);
-                    rh[m] = nrh;
-                    rq[m] = nrq;
-                }
-            }
+            };
+            if (interior_thread) update(std::true_type{});
+            else if (a0 < nx) update(std::false_type{});
         }   // sub-steps
 
         // ---- action epilogue: obs, reward, guards -----------------------------------------
@@ -372,6 +387,10 @@ public:
         BEACON_SHK_TRY(4, 256, 2)
         BEACON_SHK_TRY(6, 256, 2)
         BEACON_SHK_TRY(8, 192, 2)
+        BEACON_SHK_TRY(5, 288, 2)
+        BEACON_SHK_TRY(7, 224, 2)
+        BEACON_SHK_TRY(9, 160, 3)
+        BEACON_SHK_TRY(9, 160, 2)
         BEACON_SHK_TRY(4, 384, 1)
         BEACON_SHK_TRY(11, 128, 3)
         BEACON_SHK_TRY(8, 256, 1)

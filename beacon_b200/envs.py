@@ -251,7 +251,7 @@ class _Mac(_Single):
 class rayleigh(_Mac):
     """rayleigh.py:16-275."""
     _name = "rayleigh"
-    _fields = ("u", "v", "p", "T", "us", "vs", "a")
+    _fields = ("u", "v", "p", "T", "a")
 
     def __init__(self, cpu=0, init=True, L=1.0, H=1.0, n_sgts=10, ra=1.0e4, device=0, dtype=torch.float64):
         self.n_sgts = n_sgts

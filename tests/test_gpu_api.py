@@ -86,7 +86,7 @@ def test_vector_env_auto_reset():
         obs, rwd, done, trunc, info = v.step(torch.full((5,), k % 3, dtype=torch.int32))
         assert bool(done.all()) == (k == n - 1)
     assert "final_obs" in info and int(info["episode_length"][0]) == n
-    assert torch.allclose(obs[:, :3], torch.full((5, 3), 10.0, dtype=torch.float64))   # fresh episode
+    assert torch.allclose(obs[:, :3].cpu(), torch.full((5, 3), 10.0, dtype=torch.float64))   # fresh episode
     assert int(v.env.get_state("stp").max()) == 0
     obs, rwd, done, trunc, info = v.step(torch.zeros(5, dtype=torch.int32))
     assert not bool(done.any()) and int(v.episode_length[0]) == 1
