@@ -426,43 +426,58 @@ __global__ void __launch_bounds__(T) mac_kernel(const MacArgs<R> a)
 }
 
 // ---------------------------------------------------------------------------------------
-// Register-resident variant (rayleigh-sized grids: five planes fit twice per SM).
-//   * shared memory: U, V, S planes + two phi exchange planes (5 x 21.6 KB fp64) -> 2 CTAs/SM;
+// Register-resident variant (rayleigh 50x50: five planes fit twice per SM).
+//   * shared memory: two phi exchange planes (row stride LDP = 57 doubles: with 2x5 tiles laid
+//     out 10 per tile-row the 64-bit bank index of a lane's tile origin is 5*lane mod 16 ->
+//     conflict free) + U, V, S planes (stride NY+2) = 112 KB -> 2 CTAs/SM;
+//   * grid size is a template parameter: every plane access of a thread is base register +
+//     immediate offset;
 //   * each thread keeps phi AND the Poisson right-hand side of its TI x TJ tile in registers for
-//     the whole solve; a sweep reads only the 2(TI+TJ) halo values from the exchange plane,
-//     writes its tile (and the ghost copies it owns) to the other plane: one __syncthreads;
+//     the whole solve; a sweep reads only the 2(TI+TJ) halo values from the exchange plane and
+//     writes its tile (+ the ghost copies it owns) to the other plane: one __syncthreads;
 //   * predictor output (us, vs) is staged in registers over one barrier and then overwrites U, V
-//     in place (old u, v are dead after the predictor; wall entries are 0 in both), the corrector
-//     is then a pointwise in-place update; p stays in L2-resident global memory;
-//   * the first sweep (phi = 0) needs no halo: the exchange planes are never zeroed.
+//     in place (old u, v are dead after the predictor; wall entries are 0 in both); the corrector
+//     is a pointwise in-place update; p stays in L2-resident global memory;
+//   * the first sweep (phi = 0) needs no halo: the exchange planes are never zeroed;
+//   * transport: A and B_W planes are written by all threads into the (then free) phi planes,
+//     B_S comes from V on the fly; ONE warp runs the recurrence over all rows in a single
+//     software-pipelined pass (coefficients of column j+1 are loaded while column j waits for
+//     the shuffle), critical path per column = SHFL + 2 FMA.
 // ---------------------------------------------------------------------------------------
-template <typename R, int TI, int TJ, int T>
+template <typename R, int NX, int NY, int TI, int TJ, int T>
 __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
 {
+    constexpr int LD = NY + 2, N = (NX + 2) * LD;       // field planes
+    constexpr int LDP = ((LD + 6) / 8) * 8 + 1;         // exchange planes: stride = 1 mod 8
+    constexpr int NP = (NX + 2) * LDP;
+    constexpr int TILES_J = NY / TJ, TILES = (NX / TI) * TILES_J, NW = T / 32;
+    static_assert(NX % TI == 0 && NY % TJ == 0 && TILES <= T, "tiles must cover the grid exactly");
+    static_assert(NX <= 64, "transport wavefront: two rows per lane");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ R s_part[2][T / 32];
-    __shared__ R s_seg[128];
-    __shared__ R s_act[128];
+    __shared__ R s_part[2][NW];
+    __shared__ R s_seg[32];
+    __shared__ R s_act[32];
     const int tid = threadIdx.x, b = blockIdx.x;
-    const int nx = a.nx, ny = a.ny, ld = a.ld, n = a.n;
     const bool resetting = a.mode == 1;
     if (resetting && a.mask && !a.mask[b]) return;
 
-    R *PA = reinterpret_cast<R *>(smem_raw), *PB = PA + n, *U = PB + n, *V = U + n, *S = V + n;
-    const size_t row = (size_t)b * n;
+    R *PA = reinterpret_cast<R *>(smem_raw), *PB = PA + NP, *U = PB + NP, *V = U + N, *S = V + N;
+    const size_t row = (size_t)b * N;
     R *gu = a.u + row, *gv = a.v + row, *gp = a.p + row, *gs = a.s + row;
 
-    const bool has_tile = tid < a.tiles_i * a.tiles_j;
-    const int ti = tid / a.tiles_j, tj = tid - ti * a.tiles_j;
+    const bool has_tile = tid < TILES;
+    const int ti = tid / TILES_J, tj = tid - ti * TILES_J;
     const int i0 = 1 + ti * TI, j0 = 1 + tj * TJ;
-    const bool top = has_tile && i0 == 1, bot = has_tile && i0 + TI - 1 == nx;
-    const bool lef = has_tile && j0 == 1, rig = has_tile && j0 + TJ - 1 == ny;
+    const int o = i0 * LD + j0, op = i0 * LDP + j0;     // tile origin in field / exchange planes
+    const bool top = has_tile && i0 == 1, bot = has_tile && i0 + TI - 1 == NX;
+    const bool lef = has_tile && j0 == 1, rig = has_tile && j0 + TJ - 1 == NY;
+    const R w_top = top ? R(2) : R(1), w_bot = bot ? R(2) : R(1), w_lef = lef ? R(1) : R(0), w_rig = rig ? R(1) : R(0);
 #define TILE_LOOP                                      \
     _Pragma("unroll") for (int r = 0; r < TI; r++)     \
     _Pragma("unroll") for (int k = 0; k < TJ; k++)
 
     if (resetting) {                                   // rayleigh.py:89-128
-        for (int e = tid; e < n; e += T) { gu[e] = a.u0[e]; gv[e] = a.v0[e]; gp[e] = a.p0[e]; gs[e] = a.s0[e]; }
+        for (int e = tid; e < N; e += T) { gu[e] = a.u0[e]; gv[e] = a.v0[e]; gp[e] = a.p0[e]; gs[e] = a.s0[e]; }
         for (int e = tid; e < a.n_sgts; e += T) a.a_cur[(size_t)b * a.n_sgts + e] = R(0);
         const int per_step = 3 * a.nx_obs_pts * a.ny_obs_pts;
         R *hist = a.obs_hist + (size_t)b * a.n_obs;
@@ -473,7 +488,7 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
                 int f = rem / (a.nx_obs_pts * a.ny_obs_pts), q = rem - f * (a.nx_obs_pts * a.ny_obs_pts);
                 int pi = q / a.ny_obs_pts, pj = q - pi * a.ny_obs_pts;
                 int x = a.nx_obs / 2 + pi * a.nx_obs, y = a.ny_obs / 2 + pj * a.ny_obs;
-                val = (f == 0) ? a.s0[x * ld + y] : (f == 1 ? a.u0[x * ld + y] : a.v0[x * ld + y]);
+                val = (f == 0) ? a.s0[x * LD + y] : (f == 1 ? a.u0[x * LD + y] : a.v0[x * LD + y]);
             }
             hist[e] = val;
             a.obs[(size_t)b * a.n_obs + e] = val;
@@ -481,9 +496,10 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
         if (tid == 0) a.stp[b] = 0;
         return;
     }
-    for (int e = tid; e < n; e += T) { U[e] = gu[e]; V[e] = gv[e]; S[e] = gs[e]; }
+    for (int e = tid; e < N; e += T) { U[e] = gu[e]; V[e] = gv[e]; S[e] = gs[e]; }
     int stp = a.stp[b];
     int status = 0;
+    const R dt = a.dt, inv_dx = a.inv_dx, inv_dy = a.inv_dy;
 
     for (int act = 0; act < a.n_fused; act++) {
         const size_t orow = (size_t)act * a.B + b;
@@ -502,26 +518,26 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
 
         for (int it = 0; it < a.ndt_act; it++) {
             // ---- boundary conditions, rayleigh.py:180-202 ------------------------------------------
-            for (int k = tid; k < 2 * (nx + 2) + 2 * (ny + 2); k += T) {
-                if (k < ny + 2) {
+            for (int k = tid; k < 2 * (NX + 2) + 2 * (NY + 2); k += T) {
+                if (k < NY + 2) {
                     int j = k;
-                    if (j >= 1 && j <= ny) { U[1 * ld + j] = R(0); S[0 * ld + j] = S[1 * ld + j]; }
-                    if (j >= 2 && j <= ny) V[0 * ld + j] = -V[1 * ld + j];
-                } else if (k < 2 * (ny + 2)) {
-                    int j = k - (ny + 2);
-                    if (j >= 1 && j <= ny) { U[(nx + 1) * ld + j] = R(0); S[(nx + 1) * ld + j] = S[nx * ld + j]; }
-                    if (j >= 2 && j <= ny) V[(nx + 1) * ld + j] = -V[nx * ld + j];
-                } else if (k < 2 * (ny + 2) + (nx + 2)) {
-                    int i = k - 2 * (ny + 2);
-                    if (i >= 1 && i <= nx + 1) U[i * ld + ny + 1] = (i == 1 || i == nx + 1) ? -R(0) : -U[i * ld + ny];
-                    if (i >= 1 && i <= nx) { V[i * ld + ny + 1] = R(0); S[i * ld + ny + 1] = R(2) * a.Tc - S[i * ld + ny]; }
+                    if (j >= 1 && j <= NY) { U[1 * LD + j] = R(0); S[0 * LD + j] = S[1 * LD + j]; }
+                    if (j >= 2 && j <= NY) V[0 * LD + j] = -V[1 * LD + j];
+                } else if (k < 2 * (NY + 2)) {
+                    int j = k - (NY + 2);
+                    if (j >= 1 && j <= NY) { U[(NX + 1) * LD + j] = R(0); S[(NX + 1) * LD + j] = S[NX * LD + j]; }
+                    if (j >= 2 && j <= NY) V[(NX + 1) * LD + j] = -V[NX * LD + j];
+                } else if (k < 2 * (NY + 2) + (NX + 2)) {
+                    int i = k - 2 * (NY + 2);
+                    if (i >= 1 && i <= NX + 1) U[i * LD + NY + 1] = (i == 1 || i == NX + 1) ? -R(0) : -U[i * LD + NY];
+                    if (i >= 1 && i <= NX) { V[i * LD + NY + 1] = R(0); S[i * LD + NY + 1] = R(2) * a.Tc - S[i * LD + NY]; }
                 } else {
-                    int i = k - 2 * (ny + 2) - (nx + 2);
-                    if (i >= 1 && i <= nx + 1) U[i * ld + 0] = (i == 1 || i == nx + 1) ? -R(0) : -U[i * ld + 1];
-                    if (i >= 1 && i <= nx) {
-                        V[i * ld + 1] = R(0);
+                    int i = k - 2 * (NY + 2) - (NX + 2);
+                    if (i >= 1 && i <= NX + 1) U[i * LD + 0] = (i == 1 || i == NX + 1) ? -R(0) : -U[i * LD + 1];
+                    if (i >= 1 && i <= NX) {
+                        V[i * LD + 1] = R(0);
                         int sg = (i - 1) / a.nx_sgts;
-                        if (sg < a.n_sgts) S[i * ld + 0] = R(2) * s_seg[sg] - S[i * ld + 1];
+                        if (sg < a.n_sgts) S[i * LD + 0] = R(2) * s_seg[sg] - S[i * LD + 1];
                     }
                 }
             }
@@ -530,191 +546,207 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
             // ---- predictor into registers, rayleigh.py:371-407 -----------------------------------------
             R us[TI][TJ], vs[TI][TJ];
             if (has_tile) {
+                const R *u = U + o, *v = V + o, *sc = S + o, *p = gp + o;
                 TILE_LOOP {
-                    const int i = i0 + r, j = j0 + k, e = i * ld + j;
-                    const R uc = U[e], vc = V[e], pc = gp[e];
+                    const int e = r * LD + k;
+                    const R uc = u[e], vc = v[e], pc = p[e];
                     us[r][k] = uc; vs[r][k] = vc;
-                    if (i >= 2) {
-                        R uE = R(0.5) * (U[e + ld] + uc), uW = R(0.5) * (uc + U[e - ld]);
-                        R uN = R(0.5) * (U[e + 1] + uc), uS = R(0.5) * (uc + U[e - 1]);
-                        R vN = R(0.5) * (V[e + 1] + V[e - ld + 1]), vS = R(0.5) * (vc + V[e - ld]);
-                        R conv = (uE * uE - uW * uW) * a.inv_dx + (uN * vN - uS * vS) * a.inv_dy;
-                        R diff = ((U[e + ld] - R(2) * uc + U[e - ld]) * a.inv_dx2 + (U[e + 1] - R(2) * uc + U[e - 1]) * a.inv_dy2) * a.dcoef;
-                        R pres = (pc - gp[e - ld]) * a.inv_dx;
-                        us[r][k] = uc + a.dt * (diff - conv - pres);
+                    if (r > 0 || !top) {               // i >= 2
+                        R uE = R(0.5) * (u[e + LD] + uc), uW = R(0.5) * (uc + u[e - LD]);
+                        R uN = R(0.5) * (u[e + 1] + uc), uS = R(0.5) * (uc + u[e - 1]);
+                        R vN = R(0.5) * (v[e + 1] + v[e - LD + 1]), vS = R(0.5) * (vc + v[e - LD]);
+                        R conv = (uE * uE - uW * uW) * inv_dx + (uN * vN - uS * vS) * inv_dy;
+                        R diff = ((u[e + LD] - R(2) * uc + u[e - LD]) * a.inv_dx2 + (u[e + 1] - R(2) * uc + u[e - 1]) * a.inv_dy2) * a.dcoef;
+                        R pres = (pc - p[e - LD]) * inv_dx;
+                        us[r][k] = uc + dt * (diff - conv - pres);
                     }
-                    if (j >= 2) {
-                        R vE = R(0.5) * (V[e + ld] + vc), vW = R(0.5) * (vc + V[e - ld]);
-                        R uE = R(0.5) * (U[e + ld] + U[e + ld - 1]), uW = R(0.5) * (uc + U[e - 1]);
-                        R vN = R(0.5) * (V[e + 1] + vc), vS = R(0.5) * (vc + V[e - 1]);
-                        R conv = (uE * vE - uW * vW) * a.inv_dx + (vN * vN - vS * vS) * a.inv_dy;
-                        R diff = ((V[e + ld] - R(2) * vc + V[e - ld]) * a.inv_dx2 + (V[e + 1] - R(2) * vc + V[e - 1]) * a.inv_dy2) * a.dcoef;
-                        R pres = (pc - gp[e - 1]) * a.inv_dy;
-                        vs[r][k] = vc + a.dt * (diff - conv - pres + S[e]);
+                    if (k > 0 || !lef) {               // j >= 2
+                        R vE = R(0.5) * (v[e + LD] + vc), vW = R(0.5) * (vc + v[e - LD]);
+                        R uE = R(0.5) * (u[e + LD] + u[e + LD - 1]), uW = R(0.5) * (uc + u[e - 1]);
+                        R vN = R(0.5) * (v[e + 1] + vc), vS = R(0.5) * (vc + v[e - 1]);
+                        R conv = (uE * vE - uW * vW) * inv_dx + (vN * vN - vS * vS) * inv_dy;
+                        R diff = ((v[e + LD] - R(2) * vc + v[e - LD]) * a.inv_dx2 + (v[e + 1] - R(2) * vc + v[e - 1]) * a.inv_dy2) * a.dcoef;
+                        R pres = (pc - p[e - 1]) * inv_dy;
+                        vs[r][k] = vc + dt * (diff - conv - pres + sc[e]);
                     }
                 }
             }
             __syncthreads();                       // every read of the old u, v is done
-            if (has_tile) { TILE_LOOP { const int e = (i0 + r) * ld + j0 + k; U[e] = us[r][k]; V[e] = vs[r][k]; } }
+            if (has_tile) { TILE_LOOP { U[o + r * LD + k] = us[r][k]; V[o + r * LD + k] = vs[r][k]; } }
             __syncthreads();                       // U, V now hold the starred fields (walls: 0)
 
             // ---- Poisson: rhs and phi in registers, rayleigh.py:412-456 -------------------------------
             R c[TI][TJ], phi[TI][TJ];
             if (has_tile) {
                 TILE_LOOP {
-                    const int e = (i0 + r) * ld + j0 + k;
-                    const R ue = (r < TI - 1) ? us[r + 1][k] : U[e + ld];
-                    const R vn = (k < TJ - 1) ? vs[r][k + 1] : V[e + 1];
-                    c[r][k] = ((ue - us[r][k]) * a.inv_dx + (vn - vs[r][k]) * a.inv_dy) * a.cscale;
+                    const R ue = (r < TI - 1) ? us[r + 1][k] : U[o + (r + 1) * LD + k];
+                    const R vn = (k < TJ - 1) ? vs[r][k + 1] : V[o + r * LD + k + 1];
+                    c[r][k] = ((ue - us[r][k]) * inv_dx + (vn - vs[r][k]) * inv_dy) * a.cscale;
                     phi[r][k] = R(0);
                 }
             }
-            R *pin = PA, *pout = PB;
+            R *const pa = PA + op, *const pb = PB + op;
             R err = R(1.0e10);
             int itp = 0;
             while (err > a.tol) {
+                const R *pi = (itp & 1) ? pb : pa;       // sweep 0 reads nothing and writes PB
+                R *po = (itp & 1) ? pa : pb;
                 R acc = R(0);
                 if (has_tile) {
                     R hn[TJ], hs[TJ], hw[TI], he[TI];    // halo: rows i0-1 / i0+TI, columns j0-1 / j0+TJ
                     if (itp > 0) {
 #pragma unroll
-                        for (int k = 0; k < TJ; k++) { hn[k] = pin[(i0 - 1) * ld + j0 + k]; hs[k] = pin[(i0 + TI) * ld + j0 + k]; }
+                        for (int k = 0; k < TJ; k++) { hn[k] = pi[-LDP + k]; hs[k] = pi[TI * LDP + k]; }
 #pragma unroll
-                        for (int r = 0; r < TI; r++) { hw[r] = pin[(i0 + r) * ld + j0 - 1]; he[r] = pin[(i0 + r) * ld + j0 + TJ]; }
+                        for (int r = 0; r < TI; r++) { hw[r] = pi[r * LDP - 1]; he[r] = pi[r * LDP + TJ]; }
                     } else {
 #pragma unroll
                         for (int k = 0; k < TJ; k++) { hn[k] = R(0); hs[k] = R(0); }
 #pragma unroll
                         for (int r = 0; r < TI; r++) { hw[r] = R(0); he[r] = R(0); }
                     }
-                    R nw[TI][TJ];
-                    TILE_LOOP {
-                        const R xm = (r > 0) ? phi[r - 1][k] : hn[k], xp = (r < TI - 1) ? phi[r + 1][k] : hs[k];
-                        const R ym = (k > 0) ? phi[r][k - 1] : hw[r], yp = (k < TJ - 1) ? phi[r][k + 1] : he[r];
-                        const R v = ((xp + xm) * a.dy2 + (yp + ym) * a.dx2 - c[r][k]) * a.inv_den;
-                        const R d = v - phi[r][k];
-                        R w = d * d;
-                        acc += w;
-                        if (r == 0 && top) acc += w;                 // ghost copies re-count wall cells
-                        if (r == TI - 1 && bot) acc += w;
-                        if (k == 0 && lef) acc += w;
-                        if (k == TJ - 1 && rig) acc += w;
-                        nw[r][k] = v;
+                    R nw[TI][TJ], rs[TI], cl = R(0), cr = R(0);
+#pragma unroll
+                    for (int r = 0; r < TI; r++) {
+                        R rsum = R(0);
+#pragma unroll
+                        for (int k = 0; k < TJ; k++) {
+                            const R xm = (r > 0) ? phi[r - 1][k] : hn[k], xp = (r < TI - 1) ? phi[r + 1][k] : hs[k];
+                            const R ym = (k > 0) ? phi[r][k - 1] : hw[r], yp = (k < TJ - 1) ? phi[r][k + 1] : he[r];
+                            const R v = ((xp + xm) * a.dy2 + (yp + ym) * a.dx2 - c[r][k]) * a.inv_den;
+                            const R d = v - phi[r][k];
+                            const R w = d * d;
+                            rsum += w;
+                            if (k == 0) cl += w;
+                            if (k == TJ - 1) cr += w;
+                            nw[r][k] = v;
+                        }
+                        rs[r] = rsum;
                     }
-                    TILE_LOOP { phi[r][k] = nw[r][k]; pout[(i0 + r) * ld + j0 + k] = nw[r][k]; }
+                    // residual over the ghost-inclusive array: ghost copies re-count the wall-adjacent cells
+                    R mid = R(0);
+#pragma unroll
+                    for (int r = 1; r < TI - 1; r++) mid += rs[r];
+                    acc = (TI > 1) ? (rs[0] * w_top + rs[TI - 1] * w_bot + mid) : rs[0] * (w_top + w_bot - R(1));
+                    acc += cl * w_lef + cr * w_rig;
+                    TILE_LOOP { phi[r][k] = nw[r][k]; po[r * LDP + k] = nw[r][k]; }
                     if (top) {
 #pragma unroll
-                        for (int k = 0; k < TJ; k++) pout[j0 + k] = nw[0][k];
+                        for (int k = 0; k < TJ; k++) po[-LDP + k] = nw[0][k];
                     }
                     if (bot) {
 #pragma unroll
-                        for (int k = 0; k < TJ; k++) pout[(nx + 1) * ld + j0 + k] = nw[TI - 1][k];
+                        for (int k = 0; k < TJ; k++) po[TI * LDP + k] = nw[TI - 1][k];
                     }
                     if (lef) {
 #pragma unroll
-                        for (int r = 0; r < TI; r++) pout[(i0 + r) * ld] = nw[r][0];
+                        for (int r = 0; r < TI; r++) po[r * LDP - 1] = nw[r][0];
                     }
                     if (rig) {
 #pragma unroll
-                        for (int r = 0; r < TI; r++) pout[(i0 + r) * ld + ny + 1] = nw[r][TJ - 1];
+                        for (int r = 0; r < TI; r++) po[r * LDP + TJ] = nw[r][TJ - 1];
                     }
                 }
                 acc = warp_sum(acc);
                 R *part = s_part[itp & 1];
                 if ((tid & 31) == 0) part[tid >> 5] = acc;
                 __syncthreads();
-                err = part[0];
+                {   // same pairwise order in every thread -> identical err -> uniform loop exit
+                    R q[NW];
 #pragma unroll
-                for (int w = 1; w < T / 32; w++) err += part[w];
-                R *t = pin; pin = pout; pout = t;
+                    for (int w = 0; w < NW; w++) q[w] = part[w];
+#pragma unroll
+                    for (int st = 1; st < NW; st *= 2)
+#pragma unroll
+                        for (int w = 0; w + st < NW; w += 2 * st) q[w] += q[w + st];
+                    err = q[0];
+                }
                 itp += 1;
                 if (itp > a.itmax) { status |= BEACON_STATUS_POISSON_OVERFLOW; break; }
             }
             it_total += itp;
+            const R *pf = ((itp & 1) ? pb : pa);          // plane holding the final iterate (tile-relative)
 
             // ---- p += phi (ghosts included, rayleigh.py:219) and in-place corrector (:461-464) ----------
             if (has_tile) {
+                R *p = gp + o, *u = U + o, *v = V + o;
                 TILE_LOOP {
-                    const int i = i0 + r, j = j0 + k, e = i * ld + j;
-                    gp[e] += phi[r][k];
-                    if (i >= 2) { const R pw = (r > 0) ? phi[r - 1][k] : pin[e - ld]; U[e] = U[e] - a.dt * (phi[r][k] - pw) * a.inv_dx; }
-                    if (j >= 2) { const R ps = (k > 0) ? phi[r][k - 1] : pin[e - 1]; V[e] = V[e] - a.dt * (phi[r][k] - ps) * a.inv_dy; }
+                    const int e = r * LD + k;
+                    p[e] += phi[r][k];
+                    if (r > 0 || !top) { const R pw = (r > 0) ? phi[r - 1][k] : pf[-LDP + k]; u[e] = u[e] - dt * (phi[r][k] - pw) * inv_dx; }
+                    if (k > 0 || !lef) { const R ps = (k > 0) ? phi[r][k - 1] : pf[r * LDP - 1]; v[e] = v[e] - dt * (phi[r][k] - ps) * inv_dy; }
                 }
                 if (top) {
 #pragma unroll
-                    for (int k = 0; k < TJ; k++) gp[j0 + k] += phi[0][k];
+                    for (int k = 0; k < TJ; k++) p[-LD + k] += phi[0][k];
                 }
                 if (bot) {
 #pragma unroll
-                    for (int k = 0; k < TJ; k++) gp[(nx + 1) * ld + j0 + k] += phi[TI - 1][k];
+                    for (int k = 0; k < TJ; k++) p[TI * LD + k] += phi[TI - 1][k];
                 }
                 if (lef) {
 #pragma unroll
-                    for (int r = 0; r < TI; r++) gp[(i0 + r) * ld] += phi[r][0];
+                    for (int r = 0; r < TI; r++) p[r * LD - 1] += phi[r][0];
                 }
                 if (rig) {
 #pragma unroll
-                    for (int r = 0; r < TI; r++) gp[(i0 + r) * ld + ny + 1] += phi[r][TJ - 1];
+                    for (int r = 0; r < TI; r++) p[r * LD + TJ] += phi[r][TJ - 1];
                 }
             }
             __syncthreads();
 
-            // ---- transport, rayleigh.py:469-487 (see mac_kernel for the recurrence) -------------------
+            // ---- transport, rayleigh.py:469-487:  new(i,j) = A + BW*new(i-1,j) + BS*new(i,j-1) ----------
             {
-                const int passes = a.tr_pass, rows = (nx + passes - 1) / passes;
-                R *cA = PA, *cW = PA + rows * ld, *cS = PA + 2 * rows * ld;
                 const R kx = a.tcoef * a.inv_dx2, ky = a.tcoef * a.inv_dy2;
-                for (int ps = 0; ps < passes; ps++) {
-                    const int ib = 1 + ps * rows, ie = min(nx, ib + rows - 1);
-                    if (has_tile) {
-                        TILE_LOOP {
-                            const int i = i0 + r, j = j0 + k;
-                            if (i >= ib && i <= ie) {
-                                const int e0 = i * ld + j;
-                                const R uE = U[e0 + ld], uW = U[e0], vN = V[e0 + 1], vS = V[e0];
-                                const R sc = S[e0], sE = S[e0 + ld], sN = S[e0 + 1];
-                                R diff0 = ((sE - R(2) * sc) * a.inv_dx2 + (sN - R(2) * sc) * a.inv_dy2) * a.tcoef;
-                                R conv0 = (uE * (R(0.5) * (sE + sc)) - uW * (R(0.5) * sc)) * a.inv_dx +
-                                          (vN * (R(0.5) * (sN + sc)) - vS * (R(0.5) * sc)) * a.inv_dy;
-                                const int e = (i - ib) * ld + j;
-                                cA[e] = sc + a.dt * (diff0 - conv0);
-                                cW[e] = a.dt * (kx + R(0.5) * uW * a.inv_dx);
-                                cS[e] = a.dt * (ky + R(0.5) * vS * a.inv_dy);
-                            }
-                        }
+                if (has_tile) {
+                    const R *u = U + o, *v = V + o, *sc = S + o;
+                    TILE_LOOP {
+                        const int e = r * LD + k;
+                        const R uE = u[e + LD], uW = u[e], vN = v[e + 1], vS = v[e];
+                        const R s0 = sc[e], sE = sc[e + LD], sN = sc[e + 1];
+                        R diff0 = ((sE - R(2) * s0) * a.inv_dx2 + (sN - R(2) * s0) * a.inv_dy2) * a.tcoef;
+                        R conv0 = (uE * (R(0.5) * (sE + s0)) - uW * (R(0.5) * s0)) * inv_dx + (vN * (R(0.5) * (sN + s0)) - vS * (R(0.5) * s0)) * inv_dy;
+                        pa[r * LDP + k] = s0 + dt * (diff0 - conv0);                  // A
+                        pb[r * LDP + k] = dt * (kx + R(0.5) * uW * inv_dx);           // B_W
                     }
-                    __syncthreads();
-                    if (tid < 32) {
-                        constexpr int RPL = MAC_RPL;
-                        const int lanes = (ie - ib + 1 + RPL - 1) / RPL;
-                        const int lane = tid, rb = ib + lane * RPL;
-                        R prev[RPL];
-#pragma unroll
-                        for (int q = 0; q < RPL; q++) prev[q] = (rb + q <= ie) ? S[(rb + q) * ld + 0] : R(0);
-                        R last_new = R(0);
-                        const int steps = ny + lanes - 1;
-                        for (int t = 0; t < steps; t++) {
-                            R wv = __shfl_up_sync(0xffffffffu, last_new, 1);
-                            const int j = t - lane + 1;
-                            if (lane < lanes && j >= 1 && j <= ny) {
-                                if (lane == 0) wv = S[(ib - 1) * ld + j];
-#pragma unroll
-                                for (int q = 0; q < RPL; q++) {
-                                    const int i = rb + q;
-                                    if (i <= ie) {
-                                        const int e = (i - ib) * ld + j;
-                                        R nv = (cA[e] + cS[e] * prev[q]) + cW[e] * wv;
-                                        S[i * ld + j] = nv;
-                                        prev[q] = nv;
-                                        wv = nv;
-                                    }
-                                }
-                                last_new = wv;
-                            }
-                        }
-                    }
-                    __syncthreads();
                 }
+                __syncthreads();
+                if (tid < 32) {
+                    constexpr int LANES = (NX + 1) / 2;
+                    const int lane = tid;
+                    const bool on = lane < LANES;
+                    const int r0 = 1 + 2 * lane;                   // my rows r0, r0+1
+                    const bool two = r0 + 1 <= NX;
+                    const R hk = R(0.5) * dt * inv_dy, dky = dt * ky;
+                    const int ra = on ? r0 : 1, rb2 = (on && two) ? r0 + 1 : ra;
+                    const R *A0 = PA + ra * LDP, *A1 = PA + rb2 * LDP, *W0 = PB + ra * LDP, *W1 = PB + rb2 * LDP;
+                    const R *V0 = V + ra * LD, *V1 = V + rb2 * LD;
+                    R *S0 = S + ra * LD, *S1 = S + rb2 * LD;
+                    const R *Sg = S;                               // row 0: west ghost of row 1 (lane 0)
+                    // column 1: partial sums with the south ghost (column 0, untouched by transport)
+                    R p0 = A0[1] + (dky + hk * V0[1]) * S0[0], p1 = A1[1] + (dky + hk * V1[1]) * S1[0];
+                    R w0 = W0[1], w1 = W1[1], g = Sg[1];
+                    R last_new = R(0);
+                    for (int t = 0; t < NY + LANES - 1; t++) {
+                        R wv = __shfl_up_sync(0xffffffffu, last_new, 1);
+                        const int j = t - lane + 1;
+                        const bool act_ = on && j >= 1 && j <= NY;
+                        const int jn = (act_ && j < NY) ? j + 1 : 1;               // prefetch next column
+                        const R a0n = A0[jn], a1n = A1[jn], w0n = W0[jn], w1n = W1[jn];
+                        const R s0n = dky + hk * V0[jn], s1n = dky + hk * V1[jn], gn = Sg[jn];
+                        if (act_) {
+                            if (lane == 0) wv = g;
+                            const R n0 = p0 + w0 * wv;
+                            const R n1 = p1 + w1 * n0;
+                            S0[j] = n0;
+                            if (two) S1[j] = n1;
+                            last_new = two ? n1 : n0;
+                            p0 = a0n + s0n * n0; p1 = a1n + s1n * n1;
+                            w0 = w0n; w1 = w1n; g = gn;
+                        }
+                    }
+                }
+                __syncthreads();
             }
         }   // sub-steps
 
@@ -731,19 +763,19 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
                     int f = rem / (a.nx_obs_pts * a.ny_obs_pts), q = rem - f * (a.nx_obs_pts * a.ny_obs_pts);
                     int pi = q / a.ny_obs_pts, pj = q - pi * a.ny_obs_pts;
                     int x = a.nx_obs / 2 + pi * a.nx_obs, y = a.ny_obs / 2 + pj * a.ny_obs;
-                    val = (f == 0) ? S[x * ld + y] : (f == 1 ? U[x * ld + y] : V[x * ld + y]);
+                    val = (f == 0) ? S[x * LD + y] : (f == 1 ? U[x * LD + y] : V[x * LD + y]);
                 }
                 out[e] = val;
             }
             __syncthreads();
             for (int e = tid; e < a.n_obs; e += T) hist[e] = out[e];
             bool nonfinite = false;
-            for (int e = tid; e < n; e += T) nonfinite |= !finite_(S[e]) | !finite_(U[e]) | !finite_(V[e]);
+            for (int e = tid; e < N; e += T) nonfinite |= !finite_(S[e]) | !finite_(U[e]) | !finite_(V[e]);
             if (__syncthreads_or(nonfinite ? 1 : 0)) status |= BEACON_STATUS_NONFINITE;
             if (tid == 0) {
                 R nu = R(0);
-                for (int i = 1; i <= nx; i++) nu -= (S[i * ld + 1] - a.Th) / (R(0.5) * a.dy);
-                nu /= R(nx);
+                for (int i = 1; i <= NX; i++) nu -= (S[i * LD + 1] - a.Th) / (R(0.5) * a.dy);
+                nu /= R(NX);
                 a.rwd[orow] = -nu;
                 bool horizon = stp == a.n_act - 1;
                 a.done[orow] = horizon; a.trunc[orow] = horizon;
@@ -754,7 +786,7 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
     }   // actions
 
     __syncthreads();
-    for (int e = tid; e < n; e += T) { gu[e] = U[e]; gv[e] = V[e]; gs[e] = S[e]; }
+    for (int e = tid; e < N; e += T) { gu[e] = U[e]; gv[e] = V[e]; gs[e] = S[e]; }
     if (tid == 0) { a.stp[b] = stp; if (a.status) a.status[b] = status; }
 #undef TILE_LOOP
 }
@@ -797,9 +829,10 @@ public:
         const size_t plane = (size_t)n * sizeof(R);
         int TI, TJ;
         reg_variant = false;
-        if (ray && nx % 2 == 0 && ny % 5 == 0 && (nx / 2) * (ny / 5) <= 256 && 5 * plane + 2048 <= 112 * 1024 && !getenv("BEACON_MAC_V1")) {
+        if (ray && nx == 50 && ny == 50 && sizeof(R) * (2 * 52 * 57 + 3 * 52 * 52) <= 113 * 1024 && p.n_sgts <= 32 && !getenv("BEACON_MAC_V1")) {
             // five planes fit twice per SM: register-resident phi tiles, 2 CTAs/SM
-            kernel = mac_reg_kernel<R, 2, 5, 256>; T = 256; TI = 2; TJ = 5; smem = 5 * plane; reg_variant = true;
+            kernel = mac_reg_kernel<R, 50, 50, 2, 5, 256>; T = 256; TI = 2; TJ = 5;
+            smem = sizeof(R) * (2 * 52 * 57 + 3 * 52 * 52); reg_variant = true;
         } else if (2 * plane + 1024 <= 220 * 1024 && ((nx + 3) / 4) * ((ny + 4) / 5) <= 512) {
             kernel = mac_kernel<R, 4, 5, 512, false>; T = 512; TI = 4; TJ = 5; smem = 2 * plane;
         } else
