@@ -84,8 +84,8 @@ __global__ void __launch_bounds__(T) burgers_kernel(const BurArgs<R> a)
 #pragma unroll
             for (int m = 0; m < C + 1; m++) {
                 int f = a0 - 1 + m;
-                R r = d[m] / (d[m + 1] + R(1.0e-8));
-                R phi = (r + rabs(r)) / (R(1) + r);        // van Leer
+                R r = fdiv(d[m], d[m + 1] + R(1.0e-8));
+                R phi = fdiv(r + rabs(r), R(1) + r);        // van Leer
                 if (f <= 0) phi = R(0);
                 F[m] = e[m + 1] + (R(0.5) * phi) * d[m + 1];
             }

@@ -54,6 +54,42 @@ template <> __device__ __forceinline__ float rsqrt_(float x) { return sqrtf(x); 
 
 template <typename R> __device__ __forceinline__ bool finite_(R x) { return isfinite(x); }
 
+// Branch-free division for the hot loops.  nvcc's IEEE fp64 division is a ~25-instruction
+// sequence with a range test and a call to a slow path per division: the branches stop the
+// scheduler from interleaving independent divisions and the kernels become latency bound.
+// fdiv: MUFU.RCP64H seed (>= 20 bits), two Newton steps (-> 2^-80), one multiply: error <= 1.5 ulp
+// (the parity contract is 1e-10 relative).  A zero / denormal / non-finite divisor or an
+// overflowing quotient gives NaN or inf like the IEEE sequence up to the case b = +-0 with
+// a != 0 (NaN instead of +-inf); none of the divisors on these paths can be exactly zero
+// (they are sums with a positive epsilon) and non-finite states are flagged in `status`.
+__device__ __forceinline__ double fdiv(double a, double b)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));
+    double e = fma(-b, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-b, y, 1.0);
+    y = fma(y, e, y);
+    return a * y;
+}
+__device__ __forceinline__ float fdiv(float a, float b) { return a / b; }
+
+// Branch-free square root, same idea: MUFU.RSQ64H seed, two Newton steps on 1/sqrt(x), one
+// residual correction of sqrt(x); x = 0 is mapped to 0 by a select; negative / non-finite -> NaN.
+__device__ __forceinline__ double fsqrt(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-(x * y), y, 1.0);
+    y = fma(0.5 * y, e, y);
+    e = fma(-(x * y), y, 1.0);
+    y = fma(0.5 * y, e, y);
+    double s = x * y;
+    s = fma(0.5 * y, fma(-s, s, x), s);
+    return x == 0.0 ? 0.0 : s;
+}
+__device__ __forceinline__ float fsqrt(float x) { return sqrtf(x); }
+
 template <typename T> __device__ __forceinline__ T warp_sum(T v)
 {
 #pragma unroll

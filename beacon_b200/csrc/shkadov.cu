@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(T, MINB) shkadov_kernel(const ShkArgs<R> a)
             // ---- q2h = q*q/(h+eps), shkadov.py:213 --------------------------------------
             R zv[C];
 #pragma unroll
-            for (int m = 0; m < C; m++) zv[m] = qv[m] * qv[m] / (hv[m] + a.eps);
+            for (int m = 0; m < C; m++) zv[m] = fdiv(qv[m] * qv[m], hv[m] + a.eps);
             // ---- publish chunk edges ---------------------------------------------------
             X[XH0 * T + tid] = hv[0]; X[XH1 * T + tid] = hv[1]; X[XH2 * T + tid] = hv[2];
             X[XHL2 * T + tid] = hv[C - 2]; X[XHL1 * T + tid] = hv[C - 1];
@@ -196,8 +196,8 @@ __global__ void __launch_bounds__(T, MINB) shkadov_kernel(const ShkArgs<R> a)
                     for (int k = 0; k < C + 2; k++) { dq[k] = uq[k + 1] - uq[k]; dz[k] = uz[k + 1] - uz[k]; }
 #pragma unroll
                     for (int m = 0; m < C + 1; m++) {
-                        R rqv = dq[m] / (dq[m + 1] + R(1.0e-8));
-                        R rzv = dz[m] / (dz[m + 1] + R(1.0e-8));
+                        R rqv = fdiv(dq[m], dq[m + 1] + R(1.0e-8));
+                        R rzv = fdiv(dz[m], dz[m + 1] + R(1.0e-8));
                         // minmod max(0, min(r, 1)); a NaN ratio stays NaN like np.maximum/np.minimum
                         R pq = rqv < R(0) ? R(0) : (rqv > R(1) ? R(1) : rqv);
                         R pz = rzv < R(0) ? R(0) : (rzv > R(1) ? R(1) : rzv);
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(T, MINB) shkadov_kernel(const ShkArgs<R> a)
                         if (i == nx - 2) d3 = (-uh[m] + R(3) * uh[m + 1] - R(3) * uh[m + 2] + uh[m + 3]) * a.inv_dx3;
                     }
                     const R hh = hv[m];
-                    R nrq = R(1.2) * dq2h - a.p5d * (hh * (d3 + R(1)) - qv[m] / (hh * hh + a.eps));   // rhsq(), :507-512
+                    R nrq = R(1.2) * dq2h - a.p5d * (hh * (d3 + R(1)) - fdiv(qv[m], hh * hh + a.eps));   // rhsq(), :507-512
                     if (has_jet) {
                         int k = i - a.jz0;
                         if (k >= 0 && k < a.jz_len) {
@@ -391,9 +391,12 @@ public:
         BEACON_SHK_TRY(7, 224, 2)
         BEACON_SHK_TRY(9, 160, 3)
         BEACON_SHK_TRY(9, 160, 2)
+        BEACON_SHK_TRY(4, 352, 2)
         BEACON_SHK_TRY(4, 384, 1)
         BEACON_SHK_TRY(11, 128, 3)
         BEACON_SHK_TRY(8, 256, 1)
+        BEACON_SHK_TRY(6, 512, 1)
+        BEACON_SHK_TRY(8, 384, 1)
         BEACON_SHK_TRY(12, 256, 1)
         BEACON_SHK_TRY(12, 512, 1)
 #undef BEACON_SHK_TRY

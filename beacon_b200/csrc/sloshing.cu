@@ -68,9 +68,9 @@ __global__ void __launch_bounds__(T) sloshing_kernel(const SloArgs<R> a)
             R w[C], s[C];   // w = q^2/h + g h^2/2 (:194), s = |v| + sqrt(g h) (:197-199)
 #pragma unroll
             for (int m = 0; m < C; m++) {
-                R v = q[m] / h[m];
-                w[m] = q[m] * q[m] / h[m] + a.half_g * (h[m] * h[m]);
-                s[m] = rabs(v) + rsqrt_(a.g * h[m]);
+                R v = fdiv(q[m], h[m]);
+                w[m] = fdiv(q[m] * q[m], h[m]) + a.half_g * (h[m] * h[m]);
+                s[m] = rabs(v) + fsqrt(a.g * h[m]);
             }
             X[0][tid] = h[0]; X[1][tid] = q[0]; X[2][tid] = w[0]; X[3][tid] = s[0];
             X[4][tid] = h[C - 1]; X[5][tid] = q[C - 1]; X[6][tid] = w[C - 1]; X[7][tid] = s[C - 1];

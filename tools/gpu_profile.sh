@@ -11,6 +11,6 @@ ncu --set full --clock-control none --import-source on -k regex:shkadov_kernel -
     python bench.py --steps 6 --warmup 3 $B > $OUT/prof_${TAG}_shkadov.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 12 --csv --log-file $OUT/launches_${TAG}_rayleigh.csv \
     python bench.py --env rayleigh --batch 592 --steps 3 --warmup 3 $B > $OUT/launches_${TAG}_rayleigh.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:mac_kernel -s 3 -c 1 -f -o $OUT/prof_${TAG}_rayleigh \
+ncu --set full --clock-control none --import-source on -k regex:mac_ -s 3 -c 1 -f -o $OUT/prof_${TAG}_rayleigh \
     python bench.py --env rayleigh --batch 592 --steps 2 --warmup 3 $B > $OUT/prof_${TAG}_rayleigh.log 2>&1
 ls -la $OUT
