@@ -25,7 +25,9 @@
 //   * rayleigh (50x50): all eight planes live in shared memory (173 KB fp64); mixing (100x100,
 //     83 KB per plane): phi planes in shared memory, the other planes stay in L2-resident global
 //     memory (Poisson dominates: ~21 k sweeps per action vs 250 predictor/transport passes).
+#include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -36,7 +38,7 @@ namespace beacon {
 template <typename R> struct MacArgs {
     int nx, ny, ld, n, ndt_act, n_act, kind, n_sgts, nx_sgts, itmax, tiles_i, tiles_j;
     int nx_obs_pts, ny_obs_pts, n_obs_steps, nx_obs, ny_obs, n_obs, tr_pass;
-    R dx, dy, dt, inv_dx, inv_dy, inv_dx2, inv_dy2, dx2, dy2, inv_den, cscale, dcoef, tcoef, Tc, Th, Cmax, u_max, ref_c, tol;
+    R dx, dy, dt, inv_dx, inv_dy, inv_dx2, inv_dy2, dx2, dy2, inv_den, pk1, pk2, cscale, dcoef, tcoef, Tc, Th, Cmax, u_max, ref_c, tol;
     int B, mode, n_fused;
     R *u, *v, *p, *s, *us, *vs, *cc;   // [B, n] planes (s = T or C); us/vs/cc are workspaces
     R *a_cur, *obs_hist;
@@ -48,6 +50,7 @@ template <typename R> struct MacArgs {
     uint8_t *done, *trunc;
     int32_t *status;
     int64_t *iters;
+    unsigned long long *dbg;   // optional per-phase cycle counters (BEACON_MAC_DEBUG), block 0 only
 };
 
 // numpy pairwise sum for n <= 128 (np.mean of the action vector, rayleigh.py:165)
@@ -425,6 +428,71 @@ __global__ void __launch_bounds__(T) mac_kernel(const MacArgs<R> a)
 #undef CELL_OK
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Transport wavefront (fp64), one warp, software pipelined by hand.
+//   new(i,j) = A(i,j) + B_W(i,j) new(i-1,j) + B_S(i,j) new(i,j-1),  B_S = dky + hk v(i,j)
+// Lane l owns rows 2l+1, 2l+2 and does column j = t - l + 1 at step t.  AA / WW hold A and B_W
+// as [lane][column 0..NY][row in pair] (one LDS.128 per lane and step), V and S are the
+// field planes (row stride LD).  Every address is base(lane) + step * const, so the unrolled
+// loop uses immediate offsets only; inactive steps (column outside 1..NY) run on harmless
+// in-bounds garbage and are masked by one predicate.  Per step the dependent chain is
+// SHFL + 2 DFMA; coefficients are fetched two columns ahead.  A separate (noinline) function so
+// that its register allocation is independent of the big per-env kernel around it.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 lds128_f64(uint32_t a)
+{
+    double2 v;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double lds64_f64(uint32_t a)
+{
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+
+template <int NX, int NY, int LD>
+__device__ __noinline__ void transport_wavefront_f64(uint32_t sAA, uint32_t sWW, uint32_t sV, uint32_t sS, double hk, double dky, int lane)
+{
+    constexpr int LANES = NX / 2, STEPS = NY + LANES - 1, RS = NY + 1;
+    const bool on = lane < LANES;
+    const int l = on ? lane : 0;                       // lanes beyond the last row pair mimic lane 0, predicate off
+    const uint32_t rowA = (uint32_t)(l * RS) * 16u, rowV = (uint32_t)((2 * l + 1) * LD) * 8u;
+    // column 1: partial sums with the south ghost (column 0, untouched by transport)
+    const double2 a1 = lds128_f64(sAA + rowA + 16u), w1c = lds128_f64(sWW + rowA + 16u);
+    double p0 = fma(fma(hk, lds64_f64(sV + rowV + 8u), dky), lds64_f64(sS + rowV), a1.x);
+    double p1 = fma(fma(hk, lds64_f64(sV + rowV + LD * 8u + 8u), dky), lds64_f64(sS + rowV + LD * 8u), a1.y);
+    double w0 = w1c.x, w1 = w1c.y;
+    // bases biased by -lane: element [t] is column t - l + 2 (coefficients) / t - l + 1 (store)
+    const uint32_t aA = sAA + rowA + (uint32_t)(2 - l) * 16u, aW = sWW + rowA + (uint32_t)(2 - l) * 16u;
+    const uint32_t aV = sV + rowV + (uint32_t)(2 - l) * 8u, aS = sS + rowV + (uint32_t)(1 - l) * 8u;
+    double2 an = lds128_f64(aA), wn = lds128_f64(aW);
+    double v0n = lds64_f64(aV), v1n = lds64_f64(aV + LD * 8u);
+    double last_new = 0.0;
+    const int c0 = on ? -lane : -(1 << 20);
+#pragma unroll 2
+    for (int t = 0; t < STEPS; t++) {
+        // fetch two columns ahead
+        const double2 an2 = lds128_f64(aA + (uint32_t)(t + 1) * 16u), wn2 = lds128_f64(aW + (uint32_t)(t + 1) * 16u);
+        const double v0n2 = lds64_f64(aV + (uint32_t)(t + 1) * 8u), v1n2 = lds64_f64(aV + LD * 8u + (uint32_t)(t + 1) * 8u);
+        const double wv = __shfl_up_sync(0xffffffffu, last_new, 1);
+        const int act_ = (unsigned)(c0 + t) < (unsigned)NY;
+        const double s0n = fma(hk, v0n, dky), s1n = fma(hk, v1n, dky);
+        const double n0 = fma(w0, wv, p0);
+        const double n1 = fma(w1, n0, p1);
+        last_new = n1;
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.shared.f64 [%3], %4;\n\t@q st.shared.f64 [%3+%10], %5;\n\t"
+                     "@q fma.rn.f64 %0, %6, %4, %8;\n\t@q fma.rn.f64 %1, %7, %5, %9;\n\t}"
+                     : "+d"(p0), "+d"(p1)
+                     : "r"(act_), "r"(aS + (uint32_t)t * 8u), "d"(n0), "d"(n1), "d"(s0n), "d"(s1n), "d"(an.x), "d"(an.y), "n"(LD * 8)
+                     : "memory");
+        w0 = wn.x; w1 = wn.y;
+        an = an2; wn = wn2; v0n = v0n2; v1n = v1n2;
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // Register-resident variant (rayleigh 50x50: five planes fit twice per SM).
 //   * shared memory: two phi exchange planes (row stride LDP = 57 doubles: with 2x5 tiles laid
@@ -444,7 +512,7 @@ __global__ void __launch_bounds__(T) mac_kernel(const MacArgs<R> a)
 //     software-pipelined pass (coefficients of column j+1 are loaded while column j waits for
 //     the shuffle), critical path per column = SHFL + 2 FMA.
 // ---------------------------------------------------------------------------------------
-template <typename R, int NX, int NY, int TI, int TJ, int T>
+template <typename R, int NX, int NY, int TI, int TJ, int T, bool DBG>
 __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
 {
     constexpr int LD = NY + 2, N = (NX + 2) * LD;       // field planes
@@ -500,6 +568,9 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
     int stp = a.stp[b];
     int status = 0;
     const R dt = a.dt, inv_dx = a.inv_dx, inv_dy = a.inv_dy;
+    const bool dbg = DBG && a.dbg != nullptr && b == 0 && tid == 0;
+    long long tph[DBG ? 8 : 1] = {0}, tlast = dbg ? clock64() : 0;
+#define PHASE(n) do { if (DBG && dbg) { long long tn_ = clock64(); tph[n] += tn_ - tlast; tlast = tn_; } } while (0)
 
     for (int act = 0; act < a.n_fused; act++) {
         const size_t orow = (size_t)act * a.B + b;
@@ -542,6 +613,7 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
                 }
             }
             __syncthreads();
+            PHASE(0);
 
             // ---- predictor into registers, rayleigh.py:371-407 -----------------------------------------
             R us[TI][TJ], vs[TI][TJ];
@@ -574,62 +646,54 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
             __syncthreads();                       // every read of the old u, v is done
             if (has_tile) { TILE_LOOP { U[o + r * LD + k] = us[r][k]; V[o + r * LD + k] = vs[r][k]; } }
             __syncthreads();                       // U, V now hold the starred fields (walls: 0)
+            PHASE(1);
 
             // ---- Poisson: rhs and phi in registers, rayleigh.py:412-456 -------------------------------
-            R c[TI][TJ], phi[TI][TJ];
-            if (has_tile) {
-                TILE_LOOP {
-                    const R ue = (r < TI - 1) ? us[r + 1][k] : U[o + (r + 1) * LD + k];
-                    const R vn = (k < TJ - 1) ? vs[r][k + 1] : V[o + r * LD + k + 1];
-                    c[r][k] = ((ue - us[r][k]) * inv_dx + (vn - vs[r][k]) * inv_dy) * a.cscale;
-                    phi[r][k] = R(0);
-                }
-            }
+            // phi_new = (xp+xm)*k1 + (yp+ym)*k2 + cn with k1 = dy2/(2(dx2+dy2)), k2 = dx2/(2(dx2+dy2)),
+            // cn = -b dx2 dy2/(2(dx2+dy2)): 2 DADD + 2 DFMA per cell.  phi ping-pongs between two
+            // register tiles (no copies); sweep s writes exchange plane P[s&1] and the warp partials
+            // part[s&1].  The convergence test of sweep s is evaluated AFTER sweep s+1 has been
+            // computed speculatively (its latency hides behind that work); a converged solve simply
+            // drops the speculative tile, so the sweep count is exactly the reference's.
+            R cn[TI][TJ], phi[TI][TJ], ph2[TI][TJ];
             R *const pa = PA + op, *const pb = PB + op;
-            R err = R(1.0e10);
-            int itp = 0;
-            while (err > a.tol) {
-                const R *pi = (itp & 1) ? pb : pa;       // sweep 0 reads nothing and writes PB
-                R *po = (itp & 1) ? pa : pb;
-                R acc = R(0);
+            auto tile_acc = [&](const R (&rs)[TI], const R (&dl)[TI], const R (&dr)[TI]) -> R {
+                // residual over the ghost-inclusive array: ghost copies re-count the wall-adjacent cells
+                R cl = dl[0] * dl[0], cr = dr[0] * dr[0], mid = R(0);
+#pragma unroll
+                for (int r = 1; r < TI; r++) { cl = fma(dl[r], dl[r], cl); cr = fma(dr[r], dr[r], cr); }
+#pragma unroll
+                for (int r = 1; r < TI - 1; r++) mid += rs[r];
+                R acc = (TI > 1) ? fma(rs[0], w_top, fma(rs[TI - 1], w_bot, mid)) : rs[0] * (w_top + w_bot - R(1));
+                return fma(cl, w_lef, fma(cr, w_rig, acc));
+            };
+            auto sweep = [&](const R (&in)[TI][TJ], R (&out)[TI][TJ], const R *pi) -> R {
+                R hn[TJ], hs[TJ], hw[TI], he[TI];    // halo: rows i0-1 / i0+TI, columns j0-1 / j0+TJ
+#pragma unroll
+                for (int k = 0; k < TJ; k++) { hn[k] = pi[-LDP + k]; hs[k] = pi[TI * LDP + k]; }
+#pragma unroll
+                for (int r = 0; r < TI; r++) { hw[r] = pi[r * LDP - 1]; he[r] = pi[r * LDP + TJ]; }
+                R rs[TI], dl[TI], dr[TI];
+#pragma unroll
+                for (int r = 0; r < TI; r++) {
+                    rs[r] = R(0);
+#pragma unroll
+                    for (int k = 0; k < TJ; k++) {
+                        const R xm = (r > 0) ? in[r - 1][k] : hn[k], xp = (r < TI - 1) ? in[r + 1][k] : hs[k];
+                        const R ym = (k > 0) ? in[r][k - 1] : hw[r], yp = (k < TJ - 1) ? in[r][k + 1] : he[r];
+                        const R v = fma(xp + xm, a.pk1, fma(yp + ym, a.pk2, cn[r][k]));
+                        const R d = v - in[r][k];
+                        rs[r] = fma(d, d, rs[r]);
+                        if (k == 0) dl[r] = d;
+                        if (k == TJ - 1) dr[r] = d;
+                        out[r][k] = v;
+                    }
+                }
+                return tile_acc(rs, dl, dr);
+            };
+            auto publish = [&](const R (&nw)[TI][TJ], R *po, R acc, R *part) {
                 if (has_tile) {
-                    R hn[TJ], hs[TJ], hw[TI], he[TI];    // halo: rows i0-1 / i0+TI, columns j0-1 / j0+TJ
-                    if (itp > 0) {
-#pragma unroll
-                        for (int k = 0; k < TJ; k++) { hn[k] = pi[-LDP + k]; hs[k] = pi[TI * LDP + k]; }
-#pragma unroll
-                        for (int r = 0; r < TI; r++) { hw[r] = pi[r * LDP - 1]; he[r] = pi[r * LDP + TJ]; }
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < TJ; k++) { hn[k] = R(0); hs[k] = R(0); }
-#pragma unroll
-                        for (int r = 0; r < TI; r++) { hw[r] = R(0); he[r] = R(0); }
-                    }
-                    R nw[TI][TJ], rs[TI], cl = R(0), cr = R(0);
-#pragma unroll
-                    for (int r = 0; r < TI; r++) {
-                        R rsum = R(0);
-#pragma unroll
-                        for (int k = 0; k < TJ; k++) {
-                            const R xm = (r > 0) ? phi[r - 1][k] : hn[k], xp = (r < TI - 1) ? phi[r + 1][k] : hs[k];
-                            const R ym = (k > 0) ? phi[r][k - 1] : hw[r], yp = (k < TJ - 1) ? phi[r][k + 1] : he[r];
-                            const R v = ((xp + xm) * a.dy2 + (yp + ym) * a.dx2 - c[r][k]) * a.inv_den;
-                            const R d = v - phi[r][k];
-                            const R w = d * d;
-                            rsum += w;
-                            if (k == 0) cl += w;
-                            if (k == TJ - 1) cr += w;
-                            nw[r][k] = v;
-                        }
-                        rs[r] = rsum;
-                    }
-                    // residual over the ghost-inclusive array: ghost copies re-count the wall-adjacent cells
-                    R mid = R(0);
-#pragma unroll
-                    for (int r = 1; r < TI - 1; r++) mid += rs[r];
-                    acc = (TI > 1) ? (rs[0] * w_top + rs[TI - 1] * w_bot + mid) : rs[0] * (w_top + w_bot - R(1));
-                    acc += cl * w_lef + cr * w_rig;
-                    TILE_LOOP { phi[r][k] = nw[r][k]; po[r * LDP + k] = nw[r][k]; }
+                    TILE_LOOP { po[r * LDP + k] = nw[r][k]; }
                     if (top) {
 #pragma unroll
                         for (int k = 0; k < TJ; k++) po[-LDP + k] = nw[0][k];
@@ -648,23 +712,64 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
                     }
                 }
                 acc = warp_sum(acc);
-                R *part = s_part[itp & 1];
                 if ((tid & 31) == 0) part[tid >> 5] = acc;
                 __syncthreads();
-                {   // same pairwise order in every thread -> identical err -> uniform loop exit
-                    R q[NW];
+            };
+            auto total = [&](const R *part) -> R {   // same pairwise order in every thread -> uniform decision
+                R q[NW];
 #pragma unroll
-                    for (int w = 0; w < NW; w++) q[w] = part[w];
+                for (int w = 0; w < NW; w++) q[w] = part[w];
 #pragma unroll
-                    for (int st = 1; st < NW; st *= 2)
+                for (int st = 1; st < NW; st *= 2)
 #pragma unroll
-                        for (int w = 0; w + st < NW; w += 2 * st) q[w] += q[w + st];
-                    err = q[0];
+                    for (int w = 0; w + st < NW; w += 2 * st) q[w] += q[w + st];
+                return q[0];
+            };
+            // sweep 1 starts from phi = 0: phi_1 = cn, no halo reads
+            {
+                R rs[TI], dl[TI], dr[TI];
+#pragma unroll
+                for (int r = 0; r < TI; r++) {
+                    rs[r] = R(0);
+#pragma unroll
+                    for (int k = 0; k < TJ; k++) {
+                        R cv = R(0);
+                        if (has_tile) {
+                            const R ue = (r < TI - 1) ? us[r + 1][k] : U[o + (r + 1) * LD + k];
+                            const R vn = (k < TJ - 1) ? vs[r][k + 1] : V[o + r * LD + k + 1];
+                            cv = -(((ue - us[r][k]) * inv_dx + (vn - vs[r][k]) * inv_dy) * a.cscale) * a.inv_den;
+                        }
+                        cn[r][k] = cv; phi[r][k] = cv;
+                        rs[r] = fma(cv, cv, rs[r]);
+                        if (k == 0) dl[r] = cv;
+                        if (k == TJ - 1) dr[r] = cv;
+                    }
                 }
-                itp += 1;
-                if (itp > a.itmax) { status |= BEACON_STATUS_POISSON_OVERFLOW; break; }
+                publish(phi, pb, tile_acc(rs, dl, dr), s_part[1]);
             }
+            int itp = 1;
+            bool in_ph2 = false;
+            for (;;) {
+                // phi holds sweep itp (odd, plane PB); speculate sweep itp+1 into ph2
+                R acc = R(0);
+                if (has_tile) acc = sweep(phi, ph2, pb);
+                R err = total(s_part[1]);
+                if (itp > a.itmax) { status |= BEACON_STATUS_POISSON_OVERFLOW; break; }
+                if (!(err > a.tol)) break;
+                publish(ph2, pa, acc, s_part[0]);
+                itp += 1;
+                // ph2 holds sweep itp (even, plane PA); speculate sweep itp+1 into phi
+                acc = R(0);
+                if (has_tile) acc = sweep(ph2, phi, pa);
+                err = total(s_part[0]);
+                if (itp > a.itmax) { status |= BEACON_STATUS_POISSON_OVERFLOW; in_ph2 = true; break; }
+                if (!(err > a.tol)) { in_ph2 = true; break; }
+                publish(phi, pb, acc, s_part[1]);
+                itp += 1;
+            }
+            if (in_ph2) { TILE_LOOP { phi[r][k] = ph2[r][k]; } }
             it_total += itp;
+            PHASE(2);
             const R *pf = ((itp & 1) ? pb : pa);          // plane holding the final iterate (tile-relative)
 
             // ---- p += phi (ghosts included, rayleigh.py:219) and in-place corrector (:461-464) ----------
@@ -695,58 +800,80 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
             }
             __syncthreads();
 
+            PHASE(3);
             // ---- transport, rayleigh.py:469-487:  new(i,j) = A + BW*new(i-1,j) + BS*new(i,j-1) ----------
+            // All threads write A and B_W of their cells into the (now free) exchange planes in the
+            // layout the wavefront warp wants: [lane = row pair][column][row in pair], so that one
+            // LDS.128 fetches both rows of a lane and every address is base(lane) + 16*step.  The
+            // west ghost row (i = 0, never updated) is folded into A of row 1 (B_W := 0 there).
             {
+                constexpr int RS = NY + 1;                         // columns 0..NY per row pair (0 unused)
+                static_assert(TI == 2 && NX % 2 == 0 && NX / 2 <= 32, "wavefront layout: one tile row = one lane's row pair");
+                static_assert(2 * (NX / 2) * RS <= NP, "wavefront planes must fit the exchange planes");
                 const R kx = a.tcoef * a.inv_dx2, ky = a.tcoef * a.inv_dy2;
                 if (has_tile) {
                     const R *u = U + o, *v = V + o, *sc = S + o;
+                    R *AAw = PA + (size_t)(ti * RS + j0) * 2, *WWw = PB + (size_t)(ti * RS + j0) * 2;
                     TILE_LOOP {
                         const int e = r * LD + k;
                         const R uE = u[e + LD], uW = u[e], vN = v[e + 1], vS = v[e];
                         const R s0 = sc[e], sE = sc[e + LD], sN = sc[e + 1];
                         R diff0 = ((sE - R(2) * s0) * a.inv_dx2 + (sN - R(2) * s0) * a.inv_dy2) * a.tcoef;
                         R conv0 = (uE * (R(0.5) * (sE + s0)) - uW * (R(0.5) * s0)) * inv_dx + (vN * (R(0.5) * (sN + s0)) - vS * (R(0.5) * s0)) * inv_dy;
-                        pa[r * LDP + k] = s0 + dt * (diff0 - conv0);                  // A
-                        pb[r * LDP + k] = dt * (kx + R(0.5) * uW * inv_dx);           // B_W
+                        R A = s0 + dt * (diff0 - conv0);
+                        R BW = dt * (kx + R(0.5) * uW * inv_dx);
+                        if (r == 0 && top) { A = fma(BW, sc[e - LD], A); BW = R(0); }
+                        AAw[k * 2 + r] = A;
+                        WWw[k * 2 + r] = BW;
                     }
                 }
                 __syncthreads();
+                PHASE(4);
                 if (tid < 32) {
-                    constexpr int LANES = (NX + 1) / 2;
-                    const int lane = tid;
-                    const bool on = lane < LANES;
-                    const int r0 = 1 + 2 * lane;                   // my rows r0, r0+1
-                    const bool two = r0 + 1 <= NX;
                     const R hk = R(0.5) * dt * inv_dy, dky = dt * ky;
-                    const int ra = on ? r0 : 1, rb2 = (on && two) ? r0 + 1 : ra;
-                    const R *A0 = PA + ra * LDP, *A1 = PA + rb2 * LDP, *W0 = PB + ra * LDP, *W1 = PB + rb2 * LDP;
-                    const R *V0 = V + ra * LD, *V1 = V + rb2 * LD;
-                    R *S0 = S + ra * LD, *S1 = S + rb2 * LD;
-                    const R *Sg = S;                               // row 0: west ghost of row 1 (lane 0)
-                    // column 1: partial sums with the south ghost (column 0, untouched by transport)
-                    R p0 = A0[1] + (dky + hk * V0[1]) * S0[0], p1 = A1[1] + (dky + hk * V1[1]) * S1[0];
-                    R w0 = W0[1], w1 = W1[1], g = Sg[1];
-                    R last_new = R(0);
-                    for (int t = 0; t < NY + LANES - 1; t++) {
-                        R wv = __shfl_up_sync(0xffffffffu, last_new, 1);
-                        const int j = t - lane + 1;
-                        const bool act_ = on && j >= 1 && j <= NY;
-                        const int jn = (act_ && j < NY) ? j + 1 : 1;               // prefetch next column
-                        const R a0n = A0[jn], a1n = A1[jn], w0n = W0[jn], w1n = W1[jn];
-                        const R s0n = dky + hk * V0[jn], s1n = dky + hk * V1[jn], gn = Sg[jn];
-                        if (act_) {
-                            if (lane == 0) wv = g;
-                            const R n0 = p0 + w0 * wv;
-                            const R n1 = p1 + w1 * n0;
-                            S0[j] = n0;
-                            if (two) S1[j] = n1;
-                            last_new = two ? n1 : n0;
-                            p0 = a0n + s0n * n0; p1 = a1n + s1n * n1;
-                            w0 = w0n; w1 = w1n; g = gn;
+                    if constexpr (std::is_same<R, double>::value) {
+                        transport_wavefront_f64<NX, NY, LD>((uint32_t)__cvta_generic_to_shared(PA), (uint32_t)__cvta_generic_to_shared(PB),
+                                                            (uint32_t)__cvta_generic_to_shared(V), (uint32_t)__cvta_generic_to_shared(S), hk, dky, tid);
+                    } else {
+                        // Lane l owns rows 2l+1, 2l+2 and does column j = t - l + 1 at step t.  The loop is
+                        // uniform: inactive steps (j outside 1..NY) compute on harmless in-bounds garbage and
+                        // are masked by ONE predicate (stores, partial sums); per step the dependent chain is
+                        // SHFL + 2 DFMA, the coefficients of column j+1 are fetched while it waits.
+                        constexpr int LANES = NX / 2, STEPS = NY + LANES - 1;
+                        const int lane = tid;
+                        const bool on = lane < LANES;
+                        const int l = on ? lane : 0;
+                        const R *Vr0 = V + (2 * l + 1) * LD, *Vr1 = Vr0 + LD;
+                        R *Sr0 = S + (2 * l + 1) * LD, *Sr1 = Sr0 + LD;
+                        const R *AAr = PA + (size_t)l * RS * 2, *WWr = PB + (size_t)l * RS * 2;
+                        // column 1: partial sums with the south ghost (column 0, untouched by transport)
+                        R p0 = fma(fma(hk, Vr0[1], dky), Sr0[0], AAr[2]), p1 = fma(fma(hk, Vr1[1], dky), Sr1[0], AAr[3]);
+                        R w0 = WWr[2], w1 = WWr[3];
+                        R last_new = R(0);
+                        // pointers biased by -lane: element [t] is column t - lane + 2 (prefetch) / t - lane + 1 (store)
+                        // (lanes beyond the last row pair mimic lane 0 with the predicate off)
+                        const R *An = AAr + 2 * (2 - l), *Wn = WWr + 2 * (2 - l), *V0n = Vr0 + (2 - l), *V1n = Vr1 + (2 - l);
+                        R *S0o = Sr0 + (1 - l), *S1o = Sr1 + (1 - l);
+                        const int c0 = on ? -lane : -(1 << 20);
+    #pragma unroll 2
+                        for (int t = 0; t < STEPS; t++) {
+                            const R wv = __shfl_up_sync(0xffffffffu, last_new, 1);
+                            const bool act_ = (unsigned)(c0 + t) < (unsigned)NY;
+                            const R a0n = An[2 * t], a1n = An[2 * t + 1], w0n = Wn[2 * t], w1n = Wn[2 * t + 1];
+                            const R s0n = fma(hk, V0n[t], dky), s1n = fma(hk, V1n[t], dky);
+                            const R n0 = fma(w0, wv, p0);
+                            const R n1 = fma(w1, n0, p1);
+                            last_new = n1;
+                            if (act_) {
+                                S0o[t] = n0; S1o[t] = n1;
+                                p0 = fma(s0n, n0, a0n); p1 = fma(s1n, n1, a1n);
+                            }
+                            w0 = w0n; w1 = w1n;
                         }
                     }
                 }
                 __syncthreads();
+                PHASE(5);
             }
         }   // sub-steps
 
@@ -788,6 +915,8 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
     __syncthreads();
     for (int e = tid; e < N; e += T) { gu[e] = U[e]; gv[e] = V[e]; gs[e] = S[e]; }
     if (tid == 0) { a.stp[b] = stp; if (a.status) a.status[b] = status; }
+    if (DBG && dbg) { for (int n = 0; n < (DBG ? 8 : 1); n++) a.dbg[n] += (unsigned long long)tph[n]; }
+#undef PHASE
 #undef TILE_LOOP
 }
 
@@ -795,7 +924,7 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
 template <typename R> class MacEnv : public Env {
     beacon_mac_params p;
     int kind;
-    DeviceBuffer u, v, pp, s, us, vs, cc, a_cur, a_int, obs_hist, stp, u0, v0, p0, s0;
+    DeviceBuffer u, v, pp, s, us, vs, cc, a_cur, a_int, obs_hist, stp, u0, v0, p0, s0, dbgbuf;
     MacArgs<R> base{};
     void (*kernel)(const MacArgs<R>) = nullptr;
     int T = 0;
@@ -831,7 +960,9 @@ public:
         reg_variant = false;
         if (ray && nx == 50 && ny == 50 && sizeof(R) * (2 * 52 * 57 + 3 * 52 * 52) <= 113 * 1024 && p.n_sgts <= 32 && !getenv("BEACON_MAC_V1")) {
             // five planes fit twice per SM: register-resident phi tiles, 2 CTAs/SM
-            kernel = mac_reg_kernel<R, 50, 50, 2, 5, 256>; T = 256; TI = 2; TJ = 5;
+            if (getenv("BEACON_MAC_DEBUG")) kernel = mac_reg_kernel<R, 50, 50, 2, 5, 256, true>;
+            else kernel = mac_reg_kernel<R, 50, 50, 2, 5, 256, false>;
+            T = 256; TI = 2; TJ = 5;
             smem = sizeof(R) * (2 * 52 * 57 + 3 * 52 * 52); reg_variant = true;
         } else if (2 * plane + 1024 <= 220 * 1024 && ((nx + 3) / 4) * ((ny + 4) / 5) <= 512) {
             kernel = mac_kernel<R, 4, 5, 512, false>; T = 512; TI = 4; TJ = 5; smem = 2 * plane;
@@ -863,6 +994,7 @@ public:
         a.dx = (R)dx; a.dy = (R)dy; a.dt = (R)dt; a.inv_dx = (R)(1.0 / dx); a.inv_dy = (R)(1.0 / dy);
         a.inv_dx2 = (R)(1.0 / (dx * dx)); a.inv_dy2 = (R)(1.0 / (dy * dy)); a.dx2 = (R)(dx * dx); a.dy2 = (R)(dy * dy);
         a.inv_den = (R)(0.5 / (dx * dx + dy * dy));
+        a.pk1 = (R)(dy * dy * (0.5 / (dx * dx + dy * dy))); a.pk2 = (R)(dx * dx * (0.5 / (dx * dx + dy * dy)));
         a.cscale = (R)(dx * dx * dy * dy / dt);                   // b*dx*dx*dy*dy with b = div/dt
         a.dcoef = (R)(ray ? std::sqrt(p.pr / p.ra) : 1.0 / p.re); // momentum diffusion factor
         a.tcoef = (R)(ray ? 1.0 / std::sqrt(p.pr * p.ra) : 1.0 / p.pe);
@@ -872,11 +1004,25 @@ public:
         a.a_cur = a_cur.as<R>(); a.a_int = a_int.as<int32_t>(); a.obs_hist = obs_hist.as<R>(); a.stp = stp.as<int32_t>();
         a.u0 = u0.as<R>(); a.v0 = v0.as<R>(); a.p0 = p0.as<R>(); a.s0 = s0.as<R>();
     }
-    void run(const MacArgs<R> &a, cudaStream_t st)
+    void run(const MacArgs<R> &a_, cudaStream_t st)
     {
+        MacArgs<R> a = a_;
+        static const bool debug = getenv("BEACON_MAC_DEBUG") != nullptr;
+        if (debug && reg_variant && a.mode == 0) {                       // tuning aid: cycles per phase of env 0
+            if (!dbgbuf.ptr) dbgbuf.alloc(8 * sizeof(unsigned long long));
+            BEACON_CUDA_CHECK(cudaMemsetAsync(dbgbuf.ptr, 0, 64, st));
+            a.dbg = dbgbuf.as<unsigned long long>();
+        }
         kernel<<<a.B, T, smem, st>>>(a);
         BEACON_CUDA_CHECK(cudaGetLastError());
         launches++;
+        if (debug && reg_variant && a.mode == 0) {
+            unsigned long long h[8];
+            BEACON_CUDA_CHECK(cudaMemcpyAsync(h, dbgbuf.ptr, 64, cudaMemcpyDeviceToHost, st));
+            BEACON_CUDA_CHECK(cudaStreamSynchronize(st));
+            fprintf(stderr, "[mac phases, env 0, cycles] bc %llu predictor %llu poisson %llu corrector %llu trcoef %llu wavefront %llu\n",
+                    h[0], h[1], h[2], h[3], h[4], h[5]);
+        }
     }
     void reset(const ResetArgs &r) override
     {
