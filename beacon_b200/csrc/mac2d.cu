@@ -537,8 +537,10 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
     const int ti = tid / TILES_J, tj = tid - ti * TILES_J;
     const int i0 = 1 + ti * TI, j0 = 1 + tj * TJ;
     const int o = i0 * LD + j0, op = i0 * LDP + j0;     // tile origin in field / exchange planes
+    const int opx = has_tile ? op : LDP + 1;             // threads without a tile shadow tile 0 in the sweeps (weight 0)
     const bool top = has_tile && i0 == 1, bot = has_tile && i0 + TI - 1 == NX;
     const bool lef = has_tile && j0 == 1, rig = has_tile && j0 + TJ - 1 == NY;
+    const R w_has = has_tile ? R(1) : R(0);
     const R w_top = top ? R(2) : R(1), w_bot = bot ? R(2) : R(1), w_lef = lef ? R(1) : R(0), w_rig = rig ? R(1) : R(0);
 #define TILE_LOOP                                      \
     _Pragma("unroll") for (int r = 0; r < TI; r++)     \
@@ -651,12 +653,16 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
             // ---- Poisson: rhs and phi in registers, rayleigh.py:412-456 -------------------------------
             // phi_new = (xp+xm)*k1 + (yp+ym)*k2 + cn with k1 = dy2/(2(dx2+dy2)), k2 = dx2/(2(dx2+dy2)),
             // cn = -b dx2 dy2/(2(dx2+dy2)): 2 DADD + 2 DFMA per cell.  phi ping-pongs between two
-            // register tiles (no copies); sweep s writes exchange plane P[s&1] and the warp partials
-            // part[s&1].  The convergence test of sweep s is evaluated AFTER sweep s+1 has been
-            // computed speculatively (its latency hides behind that work); a converged solve simply
-            // drops the speculative tile, so the sweep count is exactly the reference's.
+            // register tiles (no copies); sweep s writes exchange plane P[s&1] (P[1] = PB).
+            // The residual reduction is taken off the critical path: while sweep k is computed, the
+            // warp reduction of sweep k-1's residual is interleaved with it (one shuffle stage per
+            // tile column) and the CTA total of sweep k-2 (warp partials published one barrier ago) is
+            // summed; the convergence decision for sweep k-2 is made before sweep k is committed.  A
+            // converged solve drops the two speculative sweeps and re-reads its tile of phi_{k-2}
+            // from the exchange plane that still holds it, so the sweep count and the result are
+            // exactly those of the reference's `while err > tol` loop.
             R cn[TI][TJ], phi[TI][TJ], ph2[TI][TJ];
-            R *const pa = PA + op, *const pb = PB + op;
+            R *const pa = PA + opx, *const pb = PB + opx;
             auto tile_acc = [&](const R (&rs)[TI], const R (&dl)[TI], const R (&dr)[TI]) -> R {
                 // residual over the ghost-inclusive array: ghost copies re-count the wall-adjacent cells
                 R cl = dl[0] * dl[0], cr = dr[0] * dr[0], mid = R(0);
@@ -667,7 +673,9 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
                 R acc = (TI > 1) ? fma(rs[0], w_top, fma(rs[TI - 1], w_bot, mid)) : rs[0] * (w_top + w_bot - R(1));
                 return fma(cl, w_lef, fma(cr, w_rig, acc));
             };
-            auto sweep = [&](const R (&in)[TI][TJ], R (&out)[TI][TJ], const R *pi) -> R {
+            // one sweep (every thread; threads without a tile work on tile 0's addresses and weigh 0)
+            // + the warp reduction of the previous sweep's residual, one stage per column
+            auto sweep = [&](const R (&in)[TI][TJ], R (&out)[TI][TJ], const R *pi, R &wsum) -> R {
                 R hn[TJ], hs[TJ], hw[TI], he[TI];    // halo: rows i0-1 / i0+TI, columns j0-1 / j0+TJ
 #pragma unroll
                 for (int k = 0; k < TJ; k++) { hn[k] = pi[-LDP + k]; hs[k] = pi[TI * LDP + k]; }
@@ -675,10 +683,12 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
                 for (int r = 0; r < TI; r++) { hw[r] = pi[r * LDP - 1]; he[r] = pi[r * LDP + TJ]; }
                 R rs[TI], dl[TI], dr[TI];
 #pragma unroll
-                for (int r = 0; r < TI; r++) {
-                    rs[r] = R(0);
+                for (int r = 0; r < TI; r++) rs[r] = R(0);
 #pragma unroll
-                    for (int k = 0; k < TJ; k++) {
+                for (int k = 0; k < TJ; k++) {
+                    if (k < 5) wsum += __shfl_xor_sync(0xffffffffu, wsum, 16 >> k);
+#pragma unroll
+                    for (int r = 0; r < TI; r++) {
                         const R xm = (r > 0) ? in[r - 1][k] : hn[k], xp = (r < TI - 1) ? in[r + 1][k] : hs[k];
                         const R ym = (k > 0) ? in[r][k - 1] : hw[r], yp = (k < TJ - 1) ? in[r][k + 1] : he[r];
                         const R v = fma(xp + xm, a.pk1, fma(yp + ym, a.pk2, cn[r][k]));
@@ -689,9 +699,11 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
                         out[r][k] = v;
                     }
                 }
+#pragma unroll
+                for (int st = TJ; st < 5; st++) wsum += __shfl_xor_sync(0xffffffffu, wsum, 16 >> st);
                 return tile_acc(rs, dl, dr);
             };
-            auto publish = [&](const R (&nw)[TI][TJ], R *po, R acc, R *part) {
+            auto commit = [&](const R (&nw)[TI][TJ], R *po) {
                 if (has_tile) {
                     TILE_LOOP { po[r * LDP + k] = nw[r][k]; }
                     if (top) {
@@ -711,9 +723,6 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
                         for (int r = 0; r < TI; r++) po[r * LDP + TJ] = nw[r][TJ - 1];
                     }
                 }
-                acc = warp_sum(acc);
-                if ((tid & 31) == 0) part[tid >> 5] = acc;
-                __syncthreads();
             };
             auto total = [&](const R *part) -> R {   // same pairwise order in every thread -> uniform decision
                 R q[NW];
@@ -725,6 +734,7 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
                     for (int w = 0; w + st < NW; w += 2 * st) q[w] += q[w + st];
                 return q[0];
             };
+            R accp;                                       // residual of the last committed sweep (this thread)
             // sweep 1 starts from phi = 0: phi_1 = cn, no halo reads
             {
                 R rs[TI], dl[TI], dr[TI];
@@ -745,32 +755,48 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
                         if (k == TJ - 1) dr[r] = cv;
                     }
                 }
-                publish(phi, pb, tile_acc(rs, dl, dr), s_part[1]);
+                accp = tile_acc(rs, dl, dr) * w_has;
+                commit(phi, pb);
+                __syncthreads();
             }
-            int itp = 1;
-            bool in_ph2 = false;
-            for (;;) {
-                // phi holds sweep itp (odd, plane PB); speculate sweep itp+1 into ph2
-                R acc = R(0);
-                if (has_tile) acc = sweep(phi, ph2, pb);
-                R err = total(s_part[1]);
-                if (itp > a.itmax) { status |= BEACON_STATUS_POISSON_OVERFLOW; break; }
-                if (!(err > a.tol)) break;
-                publish(ph2, pa, acc, s_part[0]);
-                itp += 1;
-                // ph2 holds sweep itp (even, plane PA); speculate sweep itp+1 into phi
-                acc = R(0);
-                if (has_tile) acc = sweep(ph2, phi, pa);
-                err = total(s_part[0]);
-                if (itp > a.itmax) { status |= BEACON_STATUS_POISSON_OVERFLOW; in_ph2 = true; break; }
-                if (!(err > a.tol)) { in_ph2 = true; break; }
-                publish(phi, pb, acc, s_part[1]);
-                itp += 1;
+            // sweep 2 (speculative until sweep 1's residual is known, two barriers from now)
+            {
+                R ws = accp;
+                const R acc = sweep(phi, ph2, pb, ws) * w_has;
+                commit(ph2, pa);
+                if ((tid & 31) == 0) s_part[1][tid >> 5] = ws;
+                __syncthreads();
+                accp = acc;
             }
-            if (in_ph2) { TILE_LOOP { phi[r][k] = ph2[r][k]; } }
+            int itp;
+            const R *pf;                                  // plane holding the final iterate (tile-relative)
+            for (int k = 3;; k += 2) {
+                {   // odd k: ph2 = phi_{k-1} (in PA) -> phi = phi_k; decide on sweep k-2 (in PB)
+                    R ws = accp;
+                    const R acc = sweep(ph2, phi, pa, ws) * w_has;
+                    const R err = total(s_part[1]);
+                    if (k - 2 > a.itmax) { status |= BEACON_STATUS_POISSON_OVERFLOW; itp = k - 2; pf = pb; break; }
+                    if (!(err > a.tol)) { itp = k - 2; pf = pb; break; }
+                    commit(phi, pb);
+                    if ((tid & 31) == 0) s_part[0][tid >> 5] = ws;
+                    __syncthreads();
+                    accp = acc;
+                }
+                {   // even k+1: phi = phi_k (in PB) -> ph2 = phi_{k+1}; decide on sweep k-1 (in PA)
+                    R ws = accp;
+                    const R acc = sweep(phi, ph2, pb, ws) * w_has;
+                    const R err = total(s_part[0]);
+                    if (k - 1 > a.itmax) { status |= BEACON_STATUS_POISSON_OVERFLOW; itp = k - 1; pf = pa; break; }
+                    if (!(err > a.tol)) { itp = k - 1; pf = pa; break; }
+                    commit(ph2, pa);
+                    if ((tid & 31) == 0) s_part[1][tid >> 5] = ws;
+                    __syncthreads();
+                    accp = acc;
+                }
+            }
+            TILE_LOOP { phi[r][k] = pf[r * LDP + k]; }     // the converged iterate (its ghosts are in the plane too)
             it_total += itp;
             PHASE(2);
-            const R *pf = ((itp & 1) ? pb : pa);          // plane holding the final iterate (tile-relative)
 
             // ---- p += phi (ghosts included, rayleigh.py:219) and in-place corrector (:461-464) ----------
             if (has_tile) {
