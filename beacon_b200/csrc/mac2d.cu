@@ -472,8 +472,14 @@ __device__ __noinline__ void transport_wavefront_f64(uint32_t sAA, uint32_t sWW,
     double v0n = lds64_f64(aV), v1n = lds64_f64(aV + LD * 8u);
     double last_new = 0.0;
     const int c0 = on ? -lane : -(1 << 20);
-#pragma unroll 2
-    for (int t = 0; t < STEPS; t++) {
+    // unrolled by 6 so that the three column records in flight rotate through registers without
+    // copies; the trip count is padded to a multiple of 6 (the extra steps are inactive, their
+    // reads stay inside the planes)
+    constexpr int STEPS_PAD = ((STEPS + 5) / 6) * 6;
+    static_assert(((NX / 2 - 1) * (NY + 1) + 2 - (NX / 2 - 1) + STEPS_PAD + 1) * 2 <= (NX + 2) * (((NY + 2 + 6) / 8) * 8 + 1), "padded reads leave the A/W planes");
+    static_assert((NX - 1) * LD + 2 - (NX / 2 - 1) + STEPS_PAD + 1 + LD <= (NX + 2) * LD, "padded reads leave the V plane");
+#pragma unroll 6
+    for (int t = 0; t < STEPS_PAD; t++) {
         // fetch two columns ahead
         const double2 an2 = lds128_f64(aA + (uint32_t)(t + 1) * 16u), wn2 = lds128_f64(aW + (uint32_t)(t + 1) * 16u);
         const double v0n2 = lds64_f64(aV + (uint32_t)(t + 1) * 8u), v1n2 = lds64_f64(aV + LD * 8u + (uint32_t)(t + 1) * 8u);
@@ -567,6 +573,14 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
         return;
     }
     for (int e = tid; e < N; e += T) { U[e] = gu[e]; V[e] = gv[e]; S[e] = gs[e]; }
+    // Ghost cells of p only ever accumulate the same increments as their wall-adjacent cells (phi
+    // ghosts are copies) and never feed back: they are brought up to date once, at the end of the
+    // launch, from the launch-initial values of the adjacent cells saved in the `us` workspace plane.
+    if (has_tile && (top || bot || lef || rig)) {
+        const R *p = gp + o;
+        R *sv = a.us + row + o;
+        TILE_LOOP { sv[r * LD + k] = p[r * LD + k]; }
+    }
     int stp = a.stp[b];
     int status = 0;
     const R dt = a.dt, inv_dx = a.inv_dx, inv_dy = a.inv_dy;
@@ -652,8 +666,8 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
 
             // ---- Poisson: rhs and phi in registers, rayleigh.py:412-456 -------------------------------
             // phi_new = (xp+xm)*k1 + (yp+ym)*k2 + cn with k1 = dy2/(2(dx2+dy2)), k2 = dx2/(2(dx2+dy2)),
-            // cn = -b dx2 dy2/(2(dx2+dy2)): 2 DADD + 2 DFMA per cell.  phi ping-pongs between two
-            // register tiles (no copies); sweep s writes exchange plane P[s&1] (P[1] = PB).
+            // cn = -b dx2 dy2/(2(dx2+dy2)): 2 DADD + 2 DFMA per cell.  phi is one register tile updated
+            // in place; sweep s writes exchange plane P[s&1] (P[1] = PB).
             // The residual reduction is taken off the critical path: while sweep k is computed, the
             // warp reduction of sweep k-1's residual is interleaved with it (one shuffle stage per
             // tile column) and the CTA total of sweep k-2 (warp partials published one barrier ago) is
@@ -661,7 +675,7 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
             // converged solve drops the two speculative sweeps and re-reads its tile of phi_{k-2}
             // from the exchange plane that still holds it, so the sweep count and the result are
             // exactly those of the reference's `while err > tol` loop.
-            R cn[TI][TJ], phi[TI][TJ], ph2[TI][TJ];
+            R cn[TI][TJ], phi[TI][TJ];
             R *const pa = PA + opx, *const pb = PB + opx;
             auto tile_acc = [&](const R (&rs)[TI], const R (&dl)[TI], const R (&dr)[TI]) -> R {
                 // residual over the ghost-inclusive array: ghost copies re-count the wall-adjacent cells
@@ -675,29 +689,35 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
             };
             // one sweep (every thread; threads without a tile work on tile 0's addresses and weigh 0)
             // + the warp reduction of the previous sweep's residual, one stage per column
-            auto sweep = [&](const R (&in)[TI][TJ], R (&out)[TI][TJ], const R *pi, R &wsum) -> R {
+            auto sweep = [&](R (&ph)[TI][TJ], const R *pi, R &wsum) -> R {
+                // in place, column by column: the old values of column k-1 are kept in `po_`, column k+1
+                // is still old when column k is computed (one register tile, no copies)
                 R hn[TJ], hs[TJ], hw[TI], he[TI];    // halo: rows i0-1 / i0+TI, columns j0-1 / j0+TJ
 #pragma unroll
                 for (int k = 0; k < TJ; k++) { hn[k] = pi[-LDP + k]; hs[k] = pi[TI * LDP + k]; }
 #pragma unroll
                 for (int r = 0; r < TI; r++) { hw[r] = pi[r * LDP - 1]; he[r] = pi[r * LDP + TJ]; }
-                R rs[TI], dl[TI], dr[TI];
+                R rs[TI], dl[TI], dr[TI], po_[TI];
 #pragma unroll
-                for (int r = 0; r < TI; r++) rs[r] = R(0);
+                for (int r = 0; r < TI; r++) { rs[r] = R(0); po_[r] = hw[r]; }
 #pragma unroll
                 for (int k = 0; k < TJ; k++) {
                     if (k < 5) wsum += __shfl_xor_sync(0xffffffffu, wsum, 16 >> k);
+                    R old[TI], nv[TI];
+#pragma unroll
+                    for (int r = 0; r < TI; r++) old[r] = ph[r][k];
 #pragma unroll
                     for (int r = 0; r < TI; r++) {
-                        const R xm = (r > 0) ? in[r - 1][k] : hn[k], xp = (r < TI - 1) ? in[r + 1][k] : hs[k];
-                        const R ym = (k > 0) ? in[r][k - 1] : hw[r], yp = (k < TJ - 1) ? in[r][k + 1] : he[r];
-                        const R v = fma(xp + xm, a.pk1, fma(yp + ym, a.pk2, cn[r][k]));
-                        const R d = v - in[r][k];
+                        const R xm = (r > 0) ? old[r - 1] : hn[k], xp = (r < TI - 1) ? old[r + 1] : hs[k];
+                        const R ym = po_[r], yp = (k < TJ - 1) ? ph[r][k + 1] : he[r];
+                        nv[r] = fma(xp + xm, a.pk1, fma(yp + ym, a.pk2, cn[r][k]));
+                        const R d = nv[r] - old[r];
                         rs[r] = fma(d, d, rs[r]);
                         if (k == 0) dl[r] = d;
                         if (k == TJ - 1) dr[r] = d;
-                        out[r][k] = v;
                     }
+#pragma unroll
+                    for (int r = 0; r < TI; r++) { po_[r] = old[r]; ph[r][k] = nv[r]; }
                 }
 #pragma unroll
                 for (int st = TJ; st < 5; st++) wsum += __shfl_xor_sync(0xffffffffu, wsum, 16 >> st);
@@ -762,8 +782,8 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
             // sweep 2 (speculative until sweep 1's residual is known, two barriers from now)
             {
                 R ws = accp;
-                const R acc = sweep(phi, ph2, pb, ws) * w_has;
-                commit(ph2, pa);
+                const R acc = sweep(phi, pb, ws) * w_has;
+                commit(phi, pa);
                 if ((tid & 31) == 0) s_part[1][tid >> 5] = ws;
                 __syncthreads();
                 accp = acc;
@@ -771,9 +791,9 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
             int itp;
             const R *pf;                                  // plane holding the final iterate (tile-relative)
             for (int k = 3;; k += 2) {
-                {   // odd k: ph2 = phi_{k-1} (in PA) -> phi = phi_k; decide on sweep k-2 (in PB)
+                {   // odd k: phi_{k-1} (in PA) -> phi_k; decide on sweep k-2 (still in PB)
                     R ws = accp;
-                    const R acc = sweep(ph2, phi, pa, ws) * w_has;
+                    const R acc = sweep(phi, pa, ws) * w_has;
                     const R err = total(s_part[1]);
                     if (k - 2 > a.itmax) { status |= BEACON_STATUS_POISSON_OVERFLOW; itp = k - 2; pf = pb; break; }
                     if (!(err > a.tol)) { itp = k - 2; pf = pb; break; }
@@ -782,13 +802,13 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
                     __syncthreads();
                     accp = acc;
                 }
-                {   // even k+1: phi = phi_k (in PB) -> ph2 = phi_{k+1}; decide on sweep k-1 (in PA)
+                {   // even k+1: phi_k (in PB) -> phi_{k+1}; decide on sweep k-1 (still in PA)
                     R ws = accp;
-                    const R acc = sweep(phi, ph2, pb, ws) * w_has;
+                    const R acc = sweep(phi, pb, ws) * w_has;
                     const R err = total(s_part[0]);
                     if (k - 1 > a.itmax) { status |= BEACON_STATUS_POISSON_OVERFLOW; itp = k - 1; pf = pa; break; }
                     if (!(err > a.tol)) { itp = k - 1; pf = pa; break; }
-                    commit(ph2, pa);
+                    commit(phi, pa);
                     if ((tid & 31) == 0) s_part[1][tid >> 5] = ws;
                     __syncthreads();
                     accp = acc;
@@ -798,7 +818,7 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
             it_total += itp;
             PHASE(2);
 
-            // ---- p += phi (ghosts included, rayleigh.py:219) and in-place corrector (:461-464) ----------
+            // ---- p += phi (rayleigh.py:219; ghost cells: see the end of the launch) and in-place corrector (:461-464)
             if (has_tile) {
                 R *p = gp + o, *u = U + o, *v = V + o;
                 TILE_LOOP {
@@ -806,22 +826,6 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
                     p[e] += phi[r][k];
                     if (r > 0 || !top) { const R pw = (r > 0) ? phi[r - 1][k] : pf[-LDP + k]; u[e] = u[e] - dt * (phi[r][k] - pw) * inv_dx; }
                     if (k > 0 || !lef) { const R ps = (k > 0) ? phi[r][k - 1] : pf[r * LDP - 1]; v[e] = v[e] - dt * (phi[r][k] - ps) * inv_dy; }
-                }
-                if (top) {
-#pragma unroll
-                    for (int k = 0; k < TJ; k++) p[-LD + k] += phi[0][k];
-                }
-                if (bot) {
-#pragma unroll
-                    for (int k = 0; k < TJ; k++) p[TI * LD + k] += phi[TI - 1][k];
-                }
-                if (lef) {
-#pragma unroll
-                    for (int r = 0; r < TI; r++) p[r * LD - 1] += phi[r][0];
-                }
-                if (rig) {
-#pragma unroll
-                    for (int r = 0; r < TI; r++) p[r * LD + TJ] += phi[r][TJ - 1];
                 }
             }
             __syncthreads();
@@ -940,6 +944,26 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
 
     __syncthreads();
     for (int e = tid; e < N; e += T) { gu[e] = U[e]; gv[e] = V[e]; gs[e] = S[e]; }
+    if (has_tile && (top || bot || lef || rig)) {      // ghost cells of p += this launch's increments of the adjacent cell
+        R *p = gp + o;
+        const R *sv = a.us + row + o;
+        if (top) {
+#pragma unroll
+            for (int k = 0; k < TJ; k++) p[-LD + k] += p[k] - sv[k];
+        }
+        if (bot) {
+#pragma unroll
+            for (int k = 0; k < TJ; k++) p[TI * LD + k] += p[(TI - 1) * LD + k] - sv[(TI - 1) * LD + k];
+        }
+        if (lef) {
+#pragma unroll
+            for (int r = 0; r < TI; r++) p[r * LD - 1] += p[r * LD] - sv[r * LD];
+        }
+        if (rig) {
+#pragma unroll
+            for (int r = 0; r < TI; r++) p[r * LD + TJ] += p[r * LD + TJ - 1] - sv[r * LD + TJ - 1];
+        }
+    }
     if (tid == 0) { a.stp[b] = stp; if (a.status) a.status[b] = status; }
     if (DBG && dbg) { for (int n = 0; n < (DBG ? 8 : 1); n++) a.dbg[n] += (unsigned long long)tph[n]; }
 #undef PHASE
