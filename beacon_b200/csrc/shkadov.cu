@@ -29,7 +29,7 @@ namespace beacon {
 template <typename R> struct ShkArgs {
     // geometry / numerics
     int nx, ndt_act, n_act, n_interp, n_jets, jet_pos, jet_hw, jet_space, l_obs, n_obs, obs_stride, l_rwd;
-    int per_jet_rwd, off, jets_overlap, jz0, jz_len;
+    int per_jet_rwd, off, jets_overlap, jets_simple, jz0, jz_len;
     R inv_dx, inv_2dx3, inv_dx3, hdt, p5d, eps, jet_amp, dx, blow_lo, blow_hi, blowup_rwd;
     double sigma;
     uint64_t seed;
@@ -73,14 +73,30 @@ __global__ void __launch_bounds__(T, MINB) shkadov_kernel(const ShkArgs<R> a)
     R *s_ucur = s_jet + 2 * nj;                         // [nj]
     R *s_uprev = s_ucur + nj;                           // [nj]
     R *s_term = s_uprev + nj;                           // [nj] per-jet reward terms
-    R *s_jw = s_term + nj;                              // [jz_len] parabola weight per point of the jet zone
-    short *s_jj = reinterpret_cast<short *>(s_jw + a.jz_len);   // [jz_len] jet index or -1
+    R *s_jw = s_term + nj;                              // [C + jz_len + C] parabola weight per point of the jet zone, zero padded
+    short *s_jj = reinterpret_cast<short *>(s_jw + a.jz_len + 2 * C);   // [jz_len] jet index or -1
 
     // ---- static per-thread geometry ---------------------------------------------------
     const int a0 = tid * C - a.off;                     // first point of my chunk
     const bool has_jet = (a0 + C - 1 >= a.jz0) && (a0 < a.jz0 + a.jz_len) && nj > 0;
     const int tl = tid > 0 ? tid - 1 : 0, tr = tid < T - 1 ? tid + 1 : T - 1;
     const bool interior_thread = a0 >= 2 && a0 + C - 1 <= nx - 4;   // full stencil, all points updated
+    // Thread 0 (inlet) also takes the fast path: its differences are a few selects (phi = 0 on the
+    // faces up to lattice index 0, the first off+1 points are not updated), so that warp 0 does not
+    // execute both variants of the update every sub-step and stall the others at the barrier.
+    const bool first_fast = tid == 0 && C - 1 - a.off <= nx - 4;
+    const int zf = first_fast ? a.off + 2 : 0;          // faces m < zf have phi = 0
+    const int np = first_fast ? a.off + 1 : 0;          // points m < np are not updated
+    // jets: when consecutive jet zones are at least C-1 points apart a chunk meets at most one jet
+    int myjet = -1;
+    if (a.jets_simple && nj > 0) {
+        int j = (a0 + C - 1 - a.jz0) / a.jet_space;      // last jet starting at or before my last point
+        if (a0 + C - 1 >= a.jz0) {
+            if (j >= nj) j = nj - 1;
+            if (a0 <= a.jz0 + j * a.jet_space + 2 * a.jet_hw) myjet = j;
+        }
+    }
+    const int kb = a0 - a.jz0 + C;                       // my first point in the zero-padded weight table
     const bool edge_thread = (a0 <= 0) || (a0 <= nx - 1 && a0 + C - 1 >= nx - 1);   // owns point 0 or nx-1
 
     // jet zone tables (shkadov.py:224-232): weight v = (k-s)(e-k)/(0.25 (e-s)^2)
@@ -93,9 +109,10 @@ __global__ void __launch_bounds__(T, MINB) shkadov_kernel(const ShkArgs<R> a)
             int s = a.jz0 + j * a.jet_space, e = s + 2 * a.jet_hw;
             if (i >= s && i <= e) { jj = j; w = R((long long)(i - s) * (long long)(e - i)) / (R(0.25) * R((long long)(e - s) * (long long)(e - s))); }
         }
-        s_jw[k] = w;
+        s_jw[C + k] = w;
         s_jj[k] = (short)jj;
     }
+    for (int k = tid; k < C; k += T) { s_jw[k] = R(0); s_jw[C + a.jz_len + k] = R(0); }
 
     // ---- load state into registers ----------------------------------------------------
     R hv[C], qv[C], rh[C], rq[C];
@@ -202,6 +219,7 @@ __global__ void __launch_bounds__(T, MINB) shkadov_kernel(const ShkArgs<R> a)
                         R pq = rqv < R(0) ? R(0) : (rqv > R(1) ? R(1) : rqv);
                         R pz = rzv < R(0) ? R(0) : (rzv > R(1) ? R(1) : rzv);
                         if (!INTERIOR) { if (a0 - 1 + m <= 0) { pq = R(0); pz = R(0); } }   // phi[0] = 0
+                        else if (m < 3) { if (m < zf) { pq = R(0); pz = R(0); } }
                         Fq[m] = uq[m + 1] + (R(0.5) * pq) * dq[m + 1];
                         Fz[m] = uz[m + 1] + (R(0.5) * pz) * dz[m + 1];
                     }
@@ -221,12 +239,14 @@ __global__ void __launch_bounds__(T, MINB) shkadov_kernel(const ShkArgs<R> a)
                     }
                     const R hh = hv[m];
                     R nrq = R(1.2) * dq2h - a.p5d * (hh * (d3 + R(1)) - fdiv(qv[m], hh * hh + a.eps));   // rhsq(), :507-512
-                    if (has_jet) {
+                    if (a.jets_simple) {
+                        if (myjet >= 0) nrq += sj[myjet] * s_jw[kb + m];
+                    } else if (has_jet) {
                         int k = i - a.jz0;
                         if (k >= 0 && k < a.jz_len) {
                             if (!a.jets_overlap) {
                                 int jj = s_jj[k];
-                                if (jj >= 0) nrq += sj[jj] * s_jw[k];
+                                if (jj >= 0) nrq += sj[jj] * s_jw[C + k];
                             } else {                                             // generic: jets may overlap
                                 for (int j = 0; j < nj; j++) {
                                     int s = a.jz0 + j * a.jet_space, e = s + 2 * a.jet_hw;
@@ -236,7 +256,7 @@ __global__ void __launch_bounds__(T, MINB) shkadov_kernel(const ShkArgs<R> a)
                             }
                         }
                     }
-                    if (INTERIOR || (i >= 1 && i <= nx - 2)) {                    // adams(), :515-518
+                    if ((INTERIOR && (m >= 2 || m >= np)) || (!INTERIOR && i >= 1 && i <= nx - 2)) {   // adams(), :515-518
                         hv[m] = hh + a.hdt * (R(-3) * nrh + rh[m]);
                         qv[m] = qv[m] + a.hdt * (R(-3) * nrq + rq[m]);
                         rh[m] = nrh;
@@ -244,7 +264,7 @@ __global__ void __launch_bounds__(T, MINB) shkadov_kernel(const ShkArgs<R> a)
                     }
                 }
             };
-            if (interior_thread) update(std::true_type{});
+            if (interior_thread || first_fast) update(std::true_type{});
             else if (a0 < nx) update(std::false_type{});
         }   // sub-steps
 
@@ -418,6 +438,7 @@ public:
         BEACON_REQUIRE((size_t)T * C - a.off >= (size_t)nx, "shkadov: internal chunking error");
         a.jets_overlap = (nj > 1 && p.jet_space <= 2 * p.jet_hw) ? 1 : 0;
         a.jz0 = p.jet_pos - p.jet_hw;
+        a.jets_simple = (nj > 0 && p.jet_space > 0 && (nj == 1 || p.jet_space - 2 * p.jet_hw - 1 >= C - 1) && !a.jets_overlap) ? 1 : 0;
         a.jz_len = nj > 0 ? (nj - 1) * p.jet_space + 2 * p.jet_hw + 1 : 0;
         a.inv_dx = (R)(1.0 / p.dx); a.inv_2dx3 = (R)(1.0 / (2.0 * p.dx * p.dx * p.dx)); a.inv_dx3 = (R)(1.0 / (p.dx * p.dx * p.dx));
         a.hdt = (R)(0.5 * p.dt); a.p5d = (R)(1.0 / (5.0 * p.delta)); a.eps = (R)p.eps; a.jet_amp = (R)p.jet_amp; a.dx = (R)p.dx;
@@ -428,7 +449,7 @@ public:
         a.draws = draws.as<unsigned long long>(); a.h_init = h_init.as<R>(); a.q_init = q_init.as<R>();
         a.B = B;
 
-        smem = sizeof(R) * ((size_t)2 * XN * T + 2 * (size_t)nx + p.ndt_act + 6 * (size_t)(nj ? nj : 1) + a.jz_len) +
+        smem = sizeof(R) * ((size_t)2 * XN * T + 2 * (size_t)nx + p.ndt_act + 6 * (size_t)(nj ? nj : 1) + a.jz_len + 2 * C) +
                sizeof(short) * (size_t)a.jz_len + 16;
         BEACON_REQUIRE(smem <= 227 * 1024, "shkadov: shared-memory budget exceeded");
         BEACON_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
