@@ -73,7 +73,8 @@ __global__ void __launch_bounds__(T, MINB) shkadov_kernel(const ShkArgs<R> a)
     R *s_ucur = s_jet + 2 * nj;                         // [nj]
     R *s_uprev = s_ucur + nj;                           // [nj]
     R *s_term = s_uprev + nj;                           // [nj] per-jet reward terms
-    R *s_jw = s_term + nj;                              // [C + jz_len + C] parabola weight per point of the jet zone, zero padded
+    R *s_alpha = s_term + nj;                           // [ndt_act] min(i / n_interp, 1)
+    R *s_jw = s_alpha + a.ndt_act;                              // [C + jz_len + C] parabola weight per point of the jet zone, zero padded
     short *s_jj = reinterpret_cast<short *>(s_jw + a.jz_len + 2 * C);   // [jz_len] jet index or -1
 
     // ---- static per-thread geometry ---------------------------------------------------
@@ -113,6 +114,7 @@ __global__ void __launch_bounds__(T, MINB) shkadov_kernel(const ShkArgs<R> a)
         s_jj[k] = (short)jj;
     }
     for (int k = tid; k < C; k += T) { s_jw[k] = R(0); s_jw[C + a.jz_len + k] = R(0); }
+    for (int i = tid; i < a.ndt_act; i += T) s_alpha[i] = (R)fmin((double)i / (double)a.n_interp, 1.0);
 
     // ---- load state into registers ----------------------------------------------------
     R hv[C], qv[C], rh[C], rq[C];
@@ -180,8 +182,8 @@ __global__ void __launch_bounds__(T, MINB) shkadov_kernel(const ShkArgs<R> a)
             X[XQ0 * T + tid] = qv[0]; X[XQL2 * T + tid] = qv[C - 2]; X[XQL1 * T + tid] = qv[C - 1];
             X[XZ0 * T + tid] = zv[0]; X[XZL2 * T + tid] = zv[C - 2]; X[XZL1 * T + tid] = zv[C - 1];
             // jet amplitudes of this sub-step, shkadov.py:224-226
-            if (tid < nj || nj > T) {
-                R alpha = (R)fmin((double)it / (double)a.n_interp, 1.0);
+            if (!a.jets_simple && (tid < nj || nj > T)) {
+                R alpha = s_alpha[it];
                 for (int j = tid; j < nj; j += T)
                     s_jet[buf * nj + j] = a.jet_amp * ((R(1) - alpha) * s_uprev[j] + alpha * s_ucur[j]);
             }
@@ -226,6 +228,11 @@ __global__ void __launch_bounds__(T, MINB) shkadov_kernel(const ShkArgs<R> a)
                 }
                 // ---- rhs, jets, Adams-Bashforth ----------------------------------------
                 const R *sj = s_jet + buf * nj;
+                R myamp = R(0);                                  // shkadov.py:224-226, my jet only
+                if (a.jets_simple && myjet >= 0) {
+                    const R alpha = s_alpha[it];
+                    myamp = a.jet_amp * ((R(1) - alpha) * s_uprev[myjet] + alpha * s_ucur[myjet]);
+                }
 #pragma unroll
                 for (int m = 0; m < C; m++) {
                     const int i = a0 + m;
@@ -240,7 +247,7 @@ __global__ void __launch_bounds__(T, MINB) shkadov_kernel(const ShkArgs<R> a)
                     const R hh = hv[m];
                     R nrq = R(1.2) * dq2h - a.p5d * (hh * (d3 + R(1)) - fdiv(qv[m], hh * hh + a.eps));   // rhsq(), :507-512
                     if (a.jets_simple) {
-                        if (myjet >= 0) nrq += sj[myjet] * s_jw[kb + m];
+                        if (myjet >= 0) nrq += myamp * s_jw[kb + m];
                     } else if (has_jet) {
                         int k = i - a.jz0;
                         if (k >= 0 && k < a.jz_len) {
@@ -449,7 +456,7 @@ public:
         a.draws = draws.as<unsigned long long>(); a.h_init = h_init.as<R>(); a.q_init = q_init.as<R>();
         a.B = B;
 
-        smem = sizeof(R) * ((size_t)2 * XN * T + 2 * (size_t)nx + p.ndt_act + 6 * (size_t)(nj ? nj : 1) + a.jz_len + 2 * C) +
+        smem = sizeof(R) * ((size_t)2 * XN * T + 2 * (size_t)nx + 2 * (size_t)p.ndt_act + 6 * (size_t)(nj ? nj : 1) + a.jz_len + 2 * C) +
                sizeof(short) * (size_t)a.jz_len + 16;
         BEACON_REQUIRE(smem <= 227 * 1024, "shkadov: shared-memory budget exceeded");
         BEACON_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
