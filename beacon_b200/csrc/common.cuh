@@ -57,21 +57,32 @@ template <typename R> __device__ __forceinline__ bool finite_(R x) { return isfi
 // Branch-free division for the hot loops.  nvcc's IEEE fp64 division is a ~25-instruction
 // sequence with a range test and a call to a slow path per division: the branches stop the
 // scheduler from interleaving independent divisions and the kernels become latency bound.
-// fdiv: MUFU.RCP64H seed (>= 20 bits), two Newton steps (-> 2^-80), one multiply: error <= 1.5 ulp
-// (the parity contract is 1e-10 relative).  A zero / denormal / non-finite divisor or an
-// overflowing quotient gives NaN or inf like the IEEE sequence up to the case b = +-0 with
-// a != 0 (NaN instead of +-inf); none of the divisors on these paths can be exactly zero
-// (they are sums with a positive epsilon) and non-finite states are flagged in `status`.
+// fdiv: MUFU.RCP64H seed (measured max relative error 2^-19.9 on B200), ONE cubic step
+// y1 = y0 (1 + e + e^2), e = 1 - b y0 (error e^3 = 2^-60), one multiply: measured max error of the
+// quotient 2.2e-16 relative (1 ulp) over 2^28 random operands (tools/micro/rcpacc.cu); the parity
+// contract is 1e-10.  A zero / denormal / non-finite divisor or an overflowing quotient gives NaN
+// or inf like the IEEE sequence up to the case b = +-0 with a != 0 (NaN instead of +-inf); none of
+// the divisors on these paths can be exactly zero (they are sums with a positive epsilon) and
+// non-finite states are flagged in `status`.
 __device__ __forceinline__ double fdiv(double a, double b)
 {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));
-    double e = fma(-b, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-b, y, 1.0);
-    y = fma(y, e, y);
+    const double e = fma(-b, y, 1.0);
+    y = fma(y, fma(e, e, e), y);
     return a * y;
 }
+// clamp(r, 0, 1) = max(0, min(r, 1)) decided on the high word with integer compares (the fp64
+// pipe is the bottleneck of these kernels): sign bit -> 0, exponent >= 0 -> 1, else r.
+// -0.0 -> 0.  A NaN ratio gives 0 or 1 instead of NaN (numpy's maximum/minimum would propagate
+// it): the NaN lattice value that caused it persists and spreads through the other stencil
+// terms, and the env is flagged BEACON_STATUS_NONFINITE, so nothing is hidden.
+__device__ __forceinline__ double clamp01(double r)
+{
+    const int hi = __double2hiint(r);
+    return hi < 0 ? 0.0 : (hi >= 0x3ff00000 ? 1.0 : r);
+}
+__device__ __forceinline__ float clamp01(float r) { return r < 0.0f ? 0.0f : (r > 1.0f ? 1.0f : r); }
 __device__ __forceinline__ float fdiv(float a, float b) { return a / b; }
 
 // Branch-free square root, same idea: MUFU.RSQ64H seed, two Newton steps on 1/sqrt(x), one

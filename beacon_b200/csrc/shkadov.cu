@@ -217,9 +217,9 @@ __global__ void __launch_bounds__(T, MINB) shkadov_kernel(const ShkArgs<R> a)
                     for (int m = 0; m < C + 1; m++) {
                         R rqv = fdiv(dq[m], dq[m + 1] + R(1.0e-8));
                         R rzv = fdiv(dz[m], dz[m + 1] + R(1.0e-8));
-                        // minmod max(0, min(r, 1)); a NaN ratio stays NaN like np.maximum/np.minimum
-                        R pq = rqv < R(0) ? R(0) : (rqv > R(1) ? R(1) : rqv);
-                        R pz = rzv < R(0) ? R(0) : (rzv > R(1) ? R(1) : rzv);
+                        // minmod max(0, min(r, 1))
+                        R pq = clamp01(rqv);
+                        R pz = clamp01(rzv);
                         if (!INTERIOR) { if (a0 - 1 + m <= 0) { pq = R(0); pz = R(0); } }   // phi[0] = 0
                         else if (m < 3) { if (m < zf) { pq = R(0); pz = R(0); } }
                         Fq[m] = uq[m + 1] + (R(0.5) * pq) * dq[m + 1];
