@@ -971,6 +971,484 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
 }
 
 // ---------------------------------------------------------------------------------------
+// Three-plane transport wavefront, shared memory only (any real type):
+//   new(i,j) = A + B_W new(i-1,j) + B_S new(i,j-1)
+// AA / WW / SS hold A, B_W, B_S as [lane = row pair][column 0..NY][row in pair] at byte offsets
+// offA / offW / offS of the dynamic shared memory; the ghost row west of the first row and the
+// ghost column south of column 1 are folded into A by the threads that wrote the planes (B_W = 0
+// on the first row, B_S = 0 in column 1), so the loop is uniform: lane l does column t - l + 1
+// at step t, steps before its first column run on in-bounds garbage that the zero B_S of column 1
+// wipes out, steps after its last column are masked by the store predicate.  New values
+// overwrite A in place.  Per step: 3 x 16-byte loads, 2 shuffles, 4 FMAs, one predicated store.
+// ---------------------------------------------------------------------------------------
+template <typename R> struct vec2_of;
+template <> struct vec2_of<double> { typedef double2 type; };
+template <> struct vec2_of<float> { typedef float2 type; };
+
+template <typename R, int NY>
+__device__ __noinline__ void transport_wavefront3(uint32_t offA, uint32_t offW, uint32_t offS, int lanes, int lane)
+{
+    typedef typename vec2_of<R>::type R2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int RS = NY + 1;
+    const bool on = lane < lanes;
+    const int l = on ? lane : 0;                       // lanes beyond the last row pair mimic lane 0, stores off
+    R2 *AA = reinterpret_cast<R2 *>(smem_raw + offA) + l * RS;
+    const R2 *WW = reinterpret_cast<const R2 *>(smem_raw + offW) + l * RS, *SS = reinterpret_cast<const R2 *>(smem_raw + offS) + l * RS;
+    R p0 = AA[1].x, p1 = AA[1].y, w0 = WW[1].x, w1 = WW[1].y;
+    // biased by -lane: element [t] is column t - l + 2 (coefficients) / t - l + 1 (store)
+    const R2 *An = AA + (2 - l), *Wn = WW + (2 - l), *Sn = SS + (2 - l);
+    R2 *Out = AA + (1 - l);
+    R2 an = An[0], wn = Wn[0], sn = Sn[0];
+    R last_new = R(0);
+    const int c0 = on ? -lane : -(1 << 20);
+    const int steps = ((NY + lanes - 1 + 5) / 6) * 6;   // padded: the extra steps are masked, their reads stay in shared memory
+#pragma unroll 6
+    for (int t = 0; t < steps; t++) {
+        const R2 an2 = An[t + 1], wn2 = Wn[t + 1], sn2 = Sn[t + 1];     // two columns ahead
+        const R wv = __shfl_up_sync(0xffffffffu, last_new, 1);
+        const R n0 = fma(w0, wv, p0);
+        const R n1 = fma(w1, n0, p1);
+        last_new = n1;
+        if ((unsigned)(c0 + t) < (unsigned)NY) { R2 o; o.x = n0; o.y = n1; Out[t] = o; }
+        p0 = fma(sn.x, n0, an.x); p1 = fma(sn.y, n1, an.y);
+        w0 = wn.x; w1 = wn.y;
+        an = an2; wn = wn2; sn = sn2;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Large-grid variant (mixing 100x100): register-resident Poisson exactly as in mac_reg_kernel
+// (phi and the right-hand side of a TI x TJ tile in registers, in-place sweeps, strided exchange
+// planes, residual reduction two sweeps behind), the velocity / scalar / pressure planes stay in
+// L2-resident global memory (Poisson is > 90 % of the work: ~65 sweeps per sub-step), transport in
+// row passes through the three-plane wavefront above.  One CTA per SM.
+// ---------------------------------------------------------------------------------------
+template <typename R, int NX, int NY, int TI, int TJ, int T>
+__global__ void __launch_bounds__(T, 1) mac_big_kernel(const MacArgs<R> a)
+{
+    constexpr int LD = NY + 2, N = (NX + 2) * LD;
+    constexpr int LDP = ((LD + 6) / 8) * 8 + 1;         // exchange planes: stride = 1 mod 8
+    constexpr int NP = (NX + 2) * LDP;
+    constexpr int TILES_J = NY / TJ, TILES = (NX / TI) * TILES_J, NW = T / 32;
+    constexpr int RS = NY + 1;                          // wavefront planes: columns 0..NY per row pair
+    constexpr int PASS_ROWS = ((NX / 2 + TI - 1) / TI) * TI >= 64 ? 64 / TI * TI : ((NX / 2 + TI - 1) / TI) * TI;   // rows per transport pass
+    constexpr int PASSES = (NX + PASS_ROWS - 1) / PASS_ROWS, LANES_MAX = PASS_ROWS / 2;
+    static_assert(NX % TI == 0 && NY % TJ == 0 && TILES <= T && TI % 2 == 0, "tiles must cover the grid exactly");
+    static_assert(LANES_MAX <= 32 && 3 * (LANES_MAX * RS + 8) * 2 <= 2 * NP, "transport planes must fit the exchange planes");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(16) R s_part[2][NW];
+    __shared__ R s_red[NW];
+    __shared__ R s_seg[128];
+    __shared__ R s_act[128];
+    const int tid = threadIdx.x, b = blockIdx.x;
+    const bool resetting = a.mode == 1;
+    if (resetting && a.mask && !a.mask[b]) return;
+    const bool ray = a.kind == BEACON_RAYLEIGH;
+
+    R *PA = reinterpret_cast<R *>(smem_raw), *PB = PA + NP;
+    const size_t row = (size_t)b * N;
+    R *u = a.u + row, *v = a.v + row, *p = a.p + row, *s = a.s + row, *us = a.us + row, *vs = a.vs + row;
+
+    const bool has_tile = tid < TILES;
+    const int ti = tid / TILES_J, tj = tid - ti * TILES_J;
+    const int i0 = 1 + ti * TI, j0 = 1 + tj * TJ;
+    const int o = i0 * LD + j0, op = i0 * LDP + j0;     // tile origin in field / exchange planes
+    const int opx = has_tile ? op : LDP + 1;             // threads without a tile shadow tile 0 in the sweeps (weight 0)
+    const bool top = has_tile && i0 == 1, bot = has_tile && i0 + TI - 1 == NX;
+    const bool lef = has_tile && j0 == 1, rig = has_tile && j0 + TJ - 1 == NY;
+    const R w_has = has_tile ? R(1) : R(0);
+    // residual weights: ghost copies re-count wall-adjacent cells; mixing's j = NY+1 ghost is Dirichlet 0 (mixing.py:451)
+    const R w_top = top ? R(2) : R(1), w_bot = bot ? R(2) : R(1), w_lef = lef ? R(1) : R(0), w_rig = (rig && ray) ? R(1) : R(0);
+#define TILE_LOOP                                      \
+    _Pragma("unroll") for (int r = 0; r < TI; r++)     \
+    _Pragma("unroll") for (int k = 0; k < TJ; k++)
+    const int per_step = 3 * a.nx_obs_pts * a.ny_obs_pts;
+
+    if (resetting) {                                   // rayleigh.py:89-128, mixing.py:73-111
+        for (int e = tid; e < N; e += T) {
+            u[e] = ray ? a.u0[e] : R(0); v[e] = ray ? a.v0[e] : R(0); p[e] = ray ? a.p0[e] : R(0); s[e] = a.s0[e];
+            us[e] = R(0); vs[e] = R(0);
+        }
+        for (int e = tid; e < (ray ? a.n_sgts : 0); e += T) a.a_cur[(size_t)b * a.n_sgts + e] = R(0);
+        R *hist = a.obs_hist + (size_t)b * a.n_obs;
+        for (int e = tid; e < a.n_obs; e += T) {
+            int st = e / per_step, rem = e - st * per_step;
+            R val = R(0);
+            if (st == a.n_obs_steps - 1) {
+                int f = rem / (a.nx_obs_pts * a.ny_obs_pts), q = rem - f * (a.nx_obs_pts * a.ny_obs_pts);
+                int pi = q / a.ny_obs_pts, pj = q - pi * a.ny_obs_pts;
+                int x = a.nx_obs / 2 + pi * a.nx_obs, y = a.ny_obs / 2 + pj * a.ny_obs;
+                val = (f == 0) ? a.s0[x * LD + y] : (ray ? (f == 1 ? a.u0[x * LD + y] : a.v0[x * LD + y]) : R(0));
+            }
+            hist[e] = val;
+            a.obs[(size_t)b * a.n_obs + e] = val;
+        }
+        if (tid == 0) { a.stp[b] = 0; if (!ray) a.a_int[b] = 1; }
+        return;
+    }
+    int stp = a.stp[b];
+    int status = 0;
+    const R dt = a.dt, inv_dx = a.inv_dx, inv_dy = a.inv_dy;
+
+    for (int act = 0; act < a.n_fused; act++) {
+        const size_t orow = (size_t)act * a.B + b;
+        __syncthreads();
+        // ---- action conditioning ----------------------------------------------------------------
+        if (ray) {
+            if (tid == 0) {                                        // rayleigh.py:164-171
+                const R *ain = (const R *)a.actions + orow * a.n_sgts;
+                const int ns = a.n_sgts;
+                for (int j = 0; j < ns; j++) s_act[j] = ain[j];
+                R mean = np_pairwise_small(s_act, ns) / R(ns);
+                R m = R(1);
+                for (int j = 0; j < ns; j++) { s_act[j] = s_act[j] - mean; m = np_max(m, rabs(s_act[j]) / a.Cmax); }
+                for (int j = 0; j < ns; j++) { s_act[j] = s_act[j] / m; s_seg[j] = a.Th + s_act[j]; a.a_cur[(size_t)b * ns + j] = s_act[j]; }
+            }
+        } else if (tid == 0) {                                     // get_control, mixing.py:212-234
+            int ai = ((const int32_t *)a.actions)[orow];
+            R ut = 0, ub = 0, vl = 0, vr = 0;
+            if (ai == 0) { ub = a.u_max; ut = -a.u_max; }
+            if (ai == 1) { ub = -a.u_max; ut = a.u_max; }
+            if (ai == 2) { vr = a.u_max; vl = -a.u_max; }
+            if (ai == 3) { vr = -a.u_max; vl = a.u_max; }
+            s_seg[0] = ut; s_seg[1] = ub; s_seg[2] = vl; s_seg[3] = vr;
+            a.a_int[b] = ai;
+        }
+        __syncthreads();
+        long long it_total = 0;
+
+        for (int it = 0; it < a.ndt_act; it++) {
+            // ---- boundary conditions: rayleigh.py:180-202, mixing.py:153-171 ---------------------
+            for (int k = tid; k < 2 * (NX + 2) + 2 * (NY + 2); k += T) {
+                if (k < NY + 2) {                                  // left wall (i = 0/1), index j = k
+                    int j = k;
+                    if (j >= 1 && j <= NY) { u[1 * LD + j] = R(0); s[0 * LD + j] = s[1 * LD + j]; }
+                    if (j >= 2 && j <= NY) v[0 * LD + j] = ray ? -v[1 * LD + j] : R(2) * s_seg[2] - v[1 * LD + j];
+                } else if (k < 2 * (NY + 2)) {                     // right wall
+                    int j = k - (NY + 2);
+                    if (j >= 1 && j <= NY) { u[(NX + 1) * LD + j] = R(0); s[(NX + 1) * LD + j] = s[NX * LD + j]; }
+                    if (j >= 2 && j <= NY) v[(NX + 1) * LD + j] = ray ? -v[NX * LD + j] : R(2) * s_seg[3] - v[NX * LD + j];
+                } else if (k < 2 * (NY + 2) + (NX + 2)) {          // top wall (j = NY+1), index i
+                    int i = k - 2 * (NY + 2);
+                    if (i >= 1 && i <= NX + 1) {
+                        R ui = (i == 1 || i == NX + 1) ? R(0) : u[i * LD + NY];
+                        u[i * LD + NY + 1] = ray ? -ui : R(2) * s_seg[0] - ui;
+                    }
+                    if (i >= 1 && i <= NX) {
+                        v[i * LD + NY + 1] = R(0);
+                        s[i * LD + NY + 1] = ray ? R(2) * a.Tc - s[i * LD + NY] : s[i * LD + NY];
+                    }
+                } else {                                           // bottom wall (j = 0/1)
+                    int i = k - 2 * (NY + 2) - (NX + 2);
+                    if (i >= 1 && i <= NX + 1) {
+                        R ui = (i == 1 || i == NX + 1) ? R(0) : u[i * LD + 1];
+                        u[i * LD + 0] = ray ? -ui : R(2) * s_seg[1] - ui;
+                    }
+                    if (i >= 1 && i <= NX) {
+                        v[i * LD + 1] = R(0);
+                        if (ray) {
+                            int sg = (i - 1) / a.nx_sgts;
+                            if (sg < a.n_sgts) s[i * LD + 0] = R(2) * s_seg[sg] - s[i * LD + 1];
+                        } else s[i * LD + 0] = s[i * LD + 1];
+                    }
+                }
+            }
+            __syncthreads();
+
+            // ---- predictor: rayleigh.py:371-407, mixing.py:382-416 (us, vs in registers and in global memory) ----
+            R cn[TI][TJ], phi[TI][TJ];
+            {
+            R usr[TI][TJ], vsr[TI][TJ];
+            if (has_tile) {
+                const R *uu = u + o, *vv = v + o, *sc = s + o, *pp = p + o;
+                TILE_LOOP {
+                    const int e = r * LD + k;
+                    const R uc = uu[e], vc = vv[e], pc = pp[e];
+                    usr[r][k] = R(0); vsr[r][k] = R(0);
+                    if (r > 0 || !top) {               // i >= 2
+                        R uE = R(0.5) * (uu[e + LD] + uc), uW = R(0.5) * (uc + uu[e - LD]);
+                        R uN = R(0.5) * (uu[e + 1] + uc), uS = R(0.5) * (uc + uu[e - 1]);
+                        R vN = R(0.5) * (vv[e + 1] + vv[e - LD + 1]), vS = R(0.5) * (vc + vv[e - LD]);
+                        R conv = (uE * uE - uW * uW) * inv_dx + (uN * vN - uS * vS) * inv_dy;
+                        R diff = ((uu[e + LD] - R(2) * uc + uu[e - LD]) * a.inv_dx2 + (uu[e + 1] - R(2) * uc + uu[e - 1]) * a.inv_dy2) * a.dcoef;
+                        R pres = (pc - pp[e - LD]) * inv_dx;
+                        usr[r][k] = uc + dt * (diff - conv - pres);
+                        us[o + e] = usr[r][k];
+                    }
+                    if (k > 0 || !lef) {               // j >= 2
+                        R vE = R(0.5) * (vv[e + LD] + vc), vW = R(0.5) * (vc + vv[e - LD]);
+                        R uE = R(0.5) * (uu[e + LD] + uu[e + LD - 1]), uW = R(0.5) * (uc + uu[e - 1]);
+                        R vN = R(0.5) * (vv[e + 1] + vc), vS = R(0.5) * (vc + vv[e - 1]);
+                        R conv = (uE * vE - uW * vW) * inv_dx + (vN * vN - vS * vS) * inv_dy;
+                        R diff = ((vv[e + LD] - R(2) * vc + vv[e - LD]) * a.inv_dx2 + (vv[e + 1] - R(2) * vc + vv[e - 1]) * a.inv_dy2) * a.dcoef;
+                        R pres = (pc - pp[e - 1]) * inv_dy;
+                        R rhs = diff - conv - pres;
+                        if (ray) rhs += sc[e];
+                        vsr[r][k] = vc + dt * rhs;
+                        vs[o + e] = vsr[r][k];
+                    }
+                }
+            }
+            __syncthreads();                       // us, vs of the neighbouring tiles are visible
+            // Poisson right-hand side cn = -div(us, vs)/dt dx2 dy2 / (2 (dx2 + dy2)); phi_1 = cn
+            TILE_LOOP {
+                R cv = R(0);
+                if (has_tile) {
+                    const R ue = (r < TI - 1) ? usr[r + 1][k] : us[o + (r + 1) * LD + k];
+                    const R vn = (k < TJ - 1) ? vsr[r][k + 1] : vs[o + r * LD + k + 1];
+                    cv = -(((ue - usr[r][k]) * inv_dx + (vn - vsr[r][k]) * inv_dy) * a.cscale) * a.inv_den;
+                }
+                cn[r][k] = cv; phi[r][k] = cv;
+            }
+            }
+
+            // ---- Poisson (see mac_reg_kernel): rayleigh.py:412-456 / mixing.py:421-465 ----------------
+            R *const pa = PA + opx, *const pb = PB + opx;
+            auto tile_acc = [&](const R (&rs)[TI], const R (&dl)[TI], const R (&dr)[TI]) -> R {
+                R cl = dl[0] * dl[0], cr = dr[0] * dr[0], mid = R(0);
+#pragma unroll
+                for (int r = 1; r < TI; r++) { cl = fma(dl[r], dl[r], cl); cr = fma(dr[r], dr[r], cr); }
+#pragma unroll
+                for (int r = 1; r < TI - 1; r++) mid += rs[r];
+                R acc = (TI > 1) ? fma(rs[0], w_top, fma(rs[TI - 1], w_bot, mid)) : rs[0] * (w_top + w_bot - R(1));
+                return fma(cl, w_lef, fma(cr, w_rig, acc));
+            };
+            auto sweep = [&](R (&ph)[TI][TJ], const R *pi, R &wsum) -> R {
+                R hn[TJ], hs[TJ], hw[TI], he[TI];    // halo: rows i0-1 / i0+TI, columns j0-1 / j0+TJ
+#pragma unroll
+                for (int k = 0; k < TJ; k++) { hn[k] = pi[-LDP + k]; hs[k] = pi[TI * LDP + k]; }
+#pragma unroll
+                for (int r = 0; r < TI; r++) { hw[r] = pi[r * LDP - 1]; he[r] = pi[r * LDP + TJ]; }
+                R rs[TI], dl[TI], dr[TI], po_[TI];
+#pragma unroll
+                for (int r = 0; r < TI; r++) { rs[r] = R(0); po_[r] = hw[r]; }
+#pragma unroll
+                for (int k = 0; k < TJ; k++) {
+                    if (k < 5) wsum += __shfl_xor_sync(0xffffffffu, wsum, 16 >> k);
+                    R old[TI], nv[TI];
+#pragma unroll
+                    for (int r = 0; r < TI; r++) old[r] = ph[r][k];
+#pragma unroll
+                    for (int r = 0; r < TI; r++) {
+                        const R xm = (r > 0) ? old[r - 1] : hn[k], xp = (r < TI - 1) ? old[r + 1] : hs[k];
+                        const R ym = po_[r], yp = (k < TJ - 1) ? ph[r][k + 1] : he[r];
+                        nv[r] = fma(xp + xm, a.pk1, fma(yp + ym, a.pk2, cn[r][k]));
+                        const R d = nv[r] - old[r];
+                        rs[r] = fma(d, d, rs[r]);
+                        if (k == 0) dl[r] = d;
+                        if (k == TJ - 1) dr[r] = d;
+                    }
+#pragma unroll
+                    for (int r = 0; r < TI; r++) { po_[r] = old[r]; ph[r][k] = nv[r]; }
+                }
+#pragma unroll
+                for (int st = TJ; st < 5; st++) wsum += __shfl_xor_sync(0xffffffffu, wsum, 16 >> st);
+                return tile_acc(rs, dl, dr);
+            };
+            auto commit = [&](const R (&nw)[TI][TJ], R *po) {
+                if (has_tile) {
+                    TILE_LOOP { po[r * LDP + k] = nw[r][k]; }
+                    if (top) {
+#pragma unroll
+                        for (int k = 0; k < TJ; k++) po[-LDP + k] = nw[0][k];
+                    }
+                    if (bot) {
+#pragma unroll
+                        for (int k = 0; k < TJ; k++) po[TI * LDP + k] = nw[TI - 1][k];
+                    }
+                    if (lef) {
+#pragma unroll
+                        for (int r = 0; r < TI; r++) po[r * LDP - 1] = nw[r][0];
+                    }
+                    if (rig) {
+#pragma unroll
+                        for (int r = 0; r < TI; r++) po[r * LDP + TJ] = ray ? nw[r][TJ - 1] : R(0);
+                    }
+                }
+            };
+            auto total = [&](const R *part) -> R {   // same pairwise order in every thread -> uniform decision
+                R q[NW];
+#pragma unroll
+                for (int w = 0; w < NW; w++) q[w] = part[w];
+#pragma unroll
+                for (int st = 1; st < NW; st *= 2)
+#pragma unroll
+                    for (int w = 0; w + st < NW; w += 2 * st) q[w] += q[w + st];
+                return q[0];
+            };
+            R accp;
+            {   // sweep 1 starts from phi = 0: phi_1 = cn, no halo reads
+                R rs[TI], dl[TI], dr[TI];
+#pragma unroll
+                for (int r = 0; r < TI; r++) {
+                    rs[r] = R(0);
+#pragma unroll
+                    for (int k = 0; k < TJ; k++) {
+                        const R cv = cn[r][k];
+                        rs[r] = fma(cv, cv, rs[r]);
+                        if (k == 0) dl[r] = cv;
+                        if (k == TJ - 1) dr[r] = cv;
+                    }
+                }
+                accp = tile_acc(rs, dl, dr) * w_has;
+                commit(phi, pb);
+                __syncthreads();
+            }
+            {   // sweep 2
+                R ws = accp;
+                const R acc = sweep(phi, pb, ws) * w_has;
+                commit(phi, pa);
+                if ((tid & 31) == 0) s_part[1][tid >> 5] = ws;
+                __syncthreads();
+                accp = acc;
+            }
+            int itp;
+            const R *pf;                                  // plane holding the final iterate (tile-relative)
+            for (int k = 3;; k += 2) {
+                {   // odd k: phi_{k-1} (in PA) -> phi_k; decide on sweep k-2 (still in PB)
+                    R ws = accp;
+                    const R acc = sweep(phi, pa, ws) * w_has;
+                    const R err = total(s_part[1]);
+                    if (k - 2 > a.itmax) { status |= BEACON_STATUS_POISSON_OVERFLOW; itp = k - 2; pf = pb; break; }
+                    if (!(err > a.tol)) { itp = k - 2; pf = pb; break; }
+                    commit(phi, pb);
+                    if ((tid & 31) == 0) s_part[0][tid >> 5] = ws;
+                    __syncthreads();
+                    accp = acc;
+                }
+                {   // even k+1: phi_k (in PB) -> phi_{k+1}; decide on sweep k-1 (still in PA)
+                    R ws = accp;
+                    const R acc = sweep(phi, pb, ws) * w_has;
+                    const R err = total(s_part[0]);
+                    if (k - 1 > a.itmax) { status |= BEACON_STATUS_POISSON_OVERFLOW; itp = k - 1; pf = pa; break; }
+                    if (!(err > a.tol)) { itp = k - 1; pf = pa; break; }
+                    commit(phi, pa);
+                    if ((tid & 31) == 0) s_part[1][tid >> 5] = ws;
+                    __syncthreads();
+                    accp = acc;
+                }
+            }
+            TILE_LOOP { phi[r][k] = pf[r * LDP + k]; }     // the converged iterate (its ghosts are in the plane too)
+            it_total += itp;
+
+            // ---- p += phi (ghosts included, rayleigh.py:219 / mixing.py:188) and corrector (:461-464 / :470-473) ----
+            if (has_tile) {
+                R *pp = p + o, *uu = u + o, *vv = v + o;
+                TILE_LOOP {
+                    const int e = r * LD + k;
+                    pp[e] += phi[r][k];
+                    if (r > 0 || !top) { const R pw = (r > 0) ? phi[r - 1][k] : pf[-LDP + k]; uu[e] = us[o + e] - dt * (phi[r][k] - pw) * inv_dx; }
+                    if (k > 0 || !lef) { const R ps = (k > 0) ? phi[r][k - 1] : pf[r * LDP - 1]; vv[e] = vs[o + e] - dt * (phi[r][k] - ps) * inv_dy; }
+                }
+                if (top) {
+#pragma unroll
+                    for (int k = 0; k < TJ; k++) pp[-LD + k] += phi[0][k];
+                }
+                if (bot) {
+#pragma unroll
+                    for (int k = 0; k < TJ; k++) pp[TI * LD + k] += phi[TI - 1][k];
+                }
+                if (lef) {
+#pragma unroll
+                    for (int r = 0; r < TI; r++) pp[r * LD - 1] += phi[r][0];
+                }
+                if (rig && ray) {                       // mixing: the j = NY+1 ghost of phi is 0
+#pragma unroll
+                    for (int r = 0; r < TI; r++) pp[r * LD + TJ] += phi[r][TJ - 1];
+                }
+            }
+            __syncthreads();
+
+            // ---- transport: rayleigh.py:469-487 / mixing.py:478-495, in PASSES row blocks -------------
+            {
+                const R kx = a.tcoef * a.inv_dx2, ky = a.tcoef * a.inv_dy2;
+                constexpr uint32_t PLANE_B = (uint32_t)((LANES_MAX * RS + 8) * 2 * sizeof(R));
+                R *AA = PA, *WW = reinterpret_cast<R *>(smem_raw + PLANE_B), *SS = reinterpret_cast<R *>(smem_raw + 2 * PLANE_B);
+                for (int ps = 0; ps < PASSES; ps++) {
+                    const int ib = 1 + ps * PASS_ROWS, ie = min(NX, ib + PASS_ROWS - 1);
+                    const bool mine = has_tile && i0 >= ib && i0 <= ie;       // passes are tile aligned
+                    if (mine) {
+                        const R *uu = u + o, *vv = v + o, *sc = s + o;
+                        TILE_LOOP {
+                            const int e = r * LD + k;
+                            const R uE = uu[e + LD], uW = uu[e], vN = vv[e + 1], vS = vv[e];
+                            const R s0 = sc[e], sE = sc[e + LD], sN = sc[e + 1];
+                            R diff0 = ((sE - R(2) * s0) * a.inv_dx2 + (sN - R(2) * s0) * a.inv_dy2) * a.tcoef;
+                            R conv0 = (uE * (R(0.5) * (sE + s0)) - uW * (R(0.5) * s0)) * inv_dx + (vN * (R(0.5) * (sN + s0)) - vS * (R(0.5) * s0)) * inv_dy;
+                            R A = s0 + dt * (diff0 - conv0);
+                            R BW = dt * (kx + R(0.5) * uW * inv_dx);
+                            R BS = dt * (ky + R(0.5) * vS * inv_dy);
+                            if (k == 0 && lef) { A = fma(BS, sc[e - 1], A); BS = R(0); }                 // south ghost column
+                            if (r == 0 && i0 == ib) { A = fma(BW, sc[e - LD], A); BW = R(0); }           // row west of the pass
+                            const int idx = (((i0 - ib + r) >> 1) * RS + j0 + k) * 2 + ((i0 - ib + r) & 1);
+                            AA[idx] = A; WW[idx] = BW; SS[idx] = BS;
+                        }
+                    }
+                    __syncthreads();
+                    if (tid < 32) transport_wavefront3<R, NY>(0u, PLANE_B, 2 * PLANE_B, (ie - ib + 2) / 2, tid);
+                    __syncthreads();
+                    if (mine) {
+                        TILE_LOOP {
+                            const int idx = (((i0 - ib + r) >> 1) * RS + j0 + k) * 2 + ((i0 - ib + r) & 1);
+                            s[o + r * LD + k] = AA[idx];
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+        }   // sub-steps
+
+        // ---- observations (probe history) and reward --------------------------------------------------
+        {
+            R *hist = a.obs_hist + (size_t)b * a.n_obs;
+            R *out = a.obs + orow * a.n_obs;
+            for (int e = tid; e < a.n_obs; e += T) {              // rayleigh.py:243-262, mixing.py:237-256
+                int st = e / per_step, rem = e - st * per_step;
+                R val;
+                if (st < a.n_obs_steps - 1) val = hist[e + per_step];
+                else {
+                    int f = rem / (a.nx_obs_pts * a.ny_obs_pts), q = rem - f * (a.nx_obs_pts * a.ny_obs_pts);
+                    int pi = q / a.ny_obs_pts, pj = q - pi * a.ny_obs_pts;
+                    int x = a.nx_obs / 2 + pi * a.nx_obs, y = a.ny_obs / 2 + pj * a.ny_obs;
+                    val = (f == 0) ? s[x * LD + y] : (f == 1 ? u[x * LD + y] : v[x * LD + y]);
+                }
+                out[e] = val;
+            }
+            __syncthreads();
+            for (int e = tid; e < a.n_obs; e += T) hist[e] = out[e];
+            R rwd;
+            if (ray) {                                            // rayleigh.py:265-275 (sequential sum)
+                rwd = R(0);
+                if (tid == 0) {
+                    R nu = R(0);
+                    for (int i = 1; i <= NX; i++) nu -= (s[i * LD + 1] - a.Th) / (R(0.5) * a.dy);
+                    nu /= R(NX);
+                    rwd = -nu;
+                }
+            } else {                                              // mixing.py:259-264 (mean over the whole array)
+                R part = R(0);
+                for (int e = tid; e < N; e += T) part += rabs(s[e] - a.ref_c);
+                rwd = -(block_sum(part, s_red) / R(N));
+            }
+            bool nonfinite = false;
+            for (int e = tid; e < N; e += T) nonfinite |= !finite_(s[e]) | !finite_(u[e]) | !finite_(v[e]);
+            if (__syncthreads_or(nonfinite ? 1 : 0)) status |= BEACON_STATUS_NONFINITE;
+            if (tid == 0) {
+                a.rwd[orow] = rwd;
+                bool horizon = stp == a.n_act - 1;
+                a.done[orow] = horizon; a.trunc[orow] = horizon;
+                if (a.iters) a.iters[orow] = it_total;
+            }
+            stp += 1;
+        }
+    }   // actions
+
+    if (tid == 0) { a.stp[b] = stp; if (a.status) a.status[b] = status; }
+#undef TILE_LOOP
+}
+
+// ---------------------------------------------------------------------------------------
 template <typename R> class MacEnv : public Env {
     beacon_mac_params p;
     int kind;
@@ -1014,6 +1492,10 @@ public:
             else kernel = mac_reg_kernel<R, 50, 50, 2, 5, 256, false>;
             T = 256; TI = 2; TJ = 5;
             smem = sizeof(R) * (2 * 52 * 57 + 3 * 52 * 52); reg_variant = true;
+        } else if (nx == 100 && ny == 100 && !getenv("BEACON_MAC_V1")) {
+            // register-resident Poisson, fields in L2: one CTA of 500 tile threads per SM
+            kernel = mac_big_kernel<R, 100, 100, 4, 5, 512>; T = 512; TI = 4; TJ = 5;
+            smem = sizeof(R) * 2 * (size_t)102 * 105;
         } else if (2 * plane + 1024 <= 220 * 1024 && ((nx + 3) / 4) * ((ny + 4) / 5) <= 512) {
             kernel = mac_kernel<R, 4, 5, 512, false>; T = 512; TI = 4; TJ = 5; smem = 2 * plane;
         } else
