@@ -35,6 +35,11 @@ namespace beacon {
 
 #define MAC_RPL 2   // rows per lane in the transport wavefront
 
+// Row-pair stride (in columns) of the wavefront coefficient planes: at least NY+1 columns and
+// stride - 1 = 1 mod 8, so that the 16-byte accesses of 8 consecutive lanes (addresses
+// lane * (stride - 1) * 16 B + const) fall into 8 different 16-byte bank groups.
+constexpr int wavefront_row_stride(int ny) { return ((ny + 1 - 2 + 7) / 8) * 8 + 2; }
+
 template <typename R> struct MacArgs {
     int nx, ny, ld, n, ndt_act, n_act, kind, n_sgts, nx_sgts, itmax, tiles_i, tiles_j;
     int nx_obs_pts, ny_obs_pts, n_obs_steps, nx_obs, ny_obs, n_obs, tr_pass;
@@ -456,7 +461,7 @@ __device__ __forceinline__ double lds64_f64(uint32_t a)
 template <int NX, int NY, int LD>
 __device__ __noinline__ void transport_wavefront_f64(uint32_t sAA, uint32_t sWW, uint32_t sV, uint32_t sS, double hk, double dky, int lane)
 {
-    constexpr int LANES = NX / 2, STEPS = NY + LANES - 1, RS = NY + 1;
+    constexpr int LANES = NX / 2, STEPS = NY + LANES - 1, RS = wavefront_row_stride(NY);
     const bool on = lane < LANES;
     const int l = on ? lane : 0;                       // lanes beyond the last row pair mimic lane 0, predicate off
     const uint32_t rowA = (uint32_t)(l * RS) * 16u, rowV = (uint32_t)((2 * l + 1) * LD) * 8u;
@@ -476,7 +481,7 @@ __device__ __noinline__ void transport_wavefront_f64(uint32_t sAA, uint32_t sWW,
     // copies; the trip count is padded to a multiple of 6 (the extra steps are inactive, their
     // reads stay inside the planes)
     constexpr int STEPS_PAD = ((STEPS + 5) / 6) * 6;
-    static_assert(((NX / 2 - 1) * (NY + 1) + 2 - (NX / 2 - 1) + STEPS_PAD + 1) * 2 <= (NX + 2) * (((NY + 2 + 6) / 8) * 8 + 1), "padded reads leave the A/W planes");
+    static_assert(((NX / 2 - 1) * RS + 2 - (NX / 2 - 1) + STEPS_PAD + 1) * 2 <= (NX + 2) * (((NY + 2 + 6) / 8) * 8 + 1), "padded reads leave the A/W planes");
     static_assert((NX - 1) * LD + 2 - (NX / 2 - 1) + STEPS_PAD + 1 + LD <= (NX + 2) * LD, "padded reads leave the V plane");
 #pragma unroll 6
     for (int t = 0; t < STEPS_PAD; t++) {
@@ -837,7 +842,7 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
             // LDS.128 fetches both rows of a lane and every address is base(lane) + 16*step.  The
             // west ghost row (i = 0, never updated) is folded into A of row 1 (B_W := 0 there).
             {
-                constexpr int RS = NY + 1;                         // columns 0..NY per row pair (0 unused)
+                constexpr int RS = wavefront_row_stride(NY);       // columns 0..NY per row pair (0 unused), padded
                 static_assert(TI == 2 && NX % 2 == 0 && NX / 2 <= 32, "wavefront layout: one tile row = one lane's row pair");
                 static_assert(2 * (NX / 2) * RS <= NP, "wavefront planes must fit the exchange planes");
                 const R kx = a.tcoef * a.inv_dx2, ky = a.tcoef * a.inv_dy2;
@@ -990,7 +995,7 @@ __device__ __noinline__ void transport_wavefront3(uint32_t offA, uint32_t offW, 
 {
     typedef typename vec2_of<R>::type R2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int RS = NY + 1;
+    constexpr int RS = wavefront_row_stride(NY);
     const bool on = lane < lanes;
     const int l = on ? lane : 0;                       // lanes beyond the last row pair mimic lane 0, stores off
     R2 *AA = reinterpret_cast<R2 *>(smem_raw + offA) + l * RS;
@@ -1024,14 +1029,14 @@ __device__ __noinline__ void transport_wavefront3(uint32_t offA, uint32_t offW, 
 // L2-resident global memory (Poisson is > 90 % of the work: ~65 sweeps per sub-step), transport in
 // row passes through the three-plane wavefront above.  One CTA per SM.
 // ---------------------------------------------------------------------------------------
-template <typename R, int NX, int NY, int TI, int TJ, int T>
+template <typename R, int NX, int NY, int TI, int TJ, int T, bool DBG>
 __global__ void __launch_bounds__(T, 1) mac_big_kernel(const MacArgs<R> a)
 {
     constexpr int LD = NY + 2, N = (NX + 2) * LD;
     constexpr int LDP = ((LD + 6) / 8) * 8 + 1;         // exchange planes: stride = 1 mod 8
     constexpr int NP = (NX + 2) * LDP;
     constexpr int TILES_J = NY / TJ, TILES = (NX / TI) * TILES_J, NW = T / 32;
-    constexpr int RS = NY + 1;                          // wavefront planes: columns 0..NY per row pair
+    constexpr int RS = wavefront_row_stride(NY);        // wavefront planes: columns 0..NY per row pair, padded
     constexpr int PASS_ROWS = ((NX / 2 + TI - 1) / TI) * TI >= 64 ? 64 / TI * TI : ((NX / 2 + TI - 1) / TI) * TI;   // rows per transport pass
     constexpr int PASSES = (NX + PASS_ROWS - 1) / PASS_ROWS, LANES_MAX = PASS_ROWS / 2;
     static_assert(NX % TI == 0 && NY % TJ == 0 && TILES <= T && TI % 2 == 0, "tiles must cover the grid exactly");
@@ -1090,6 +1095,9 @@ __global__ void __launch_bounds__(T, 1) mac_big_kernel(const MacArgs<R> a)
     int stp = a.stp[b];
     int status = 0;
     const R dt = a.dt, inv_dx = a.inv_dx, inv_dy = a.inv_dy;
+    const bool dbg = DBG && a.dbg != nullptr && b == 0 && tid == 0;
+    long long tph[DBG ? 8 : 1] = {0}, tlast = dbg ? clock64() : 0;
+#define PHASE(n) do { if (DBG && dbg) { long long tn_ = clock64(); tph[n] += tn_ - tlast; tlast = tn_; } } while (0)
 
     for (int act = 0; act < a.n_fused; act++) {
         const size_t orow = (size_t)act * a.B + b;
@@ -1155,13 +1163,22 @@ __global__ void __launch_bounds__(T, 1) mac_big_kernel(const MacArgs<R> a)
                 }
             }
             __syncthreads();
+            // stage u and v (ghosts included) in the exchange planes, free until the Poisson solve: the
+            // predictor reads ~15 neighbours per cell, from shared memory instead of L2
+            static_assert(N % 2 == 0, "vectorised staging");
+            for (int e = tid; e < N / 2; e += T) {
+                reinterpret_cast<typename vec2_of<R>::type *>(PA)[e] = reinterpret_cast<const typename vec2_of<R>::type *>(u)[e];
+                reinterpret_cast<typename vec2_of<R>::type *>(PB)[e] = reinterpret_cast<const typename vec2_of<R>::type *>(v)[e];
+            }
+            __syncthreads();
+            PHASE(0);
 
             // ---- predictor: rayleigh.py:371-407, mixing.py:382-416 (us, vs in registers and in global memory) ----
             R cn[TI][TJ], phi[TI][TJ];
             {
             R usr[TI][TJ], vsr[TI][TJ];
             if (has_tile) {
-                const R *uu = u + o, *vv = v + o, *sc = s + o, *pp = p + o;
+                const R *uu = PA + o, *vv = PB + o, *sc = s + o, *pp = p + o;
                 TILE_LOOP {
                     const int e = r * LD + k;
                     const R uc = uu[e], vc = vv[e], pc = pp[e];
@@ -1203,6 +1220,7 @@ __global__ void __launch_bounds__(T, 1) mac_big_kernel(const MacArgs<R> a)
             }
             }
 
+            PHASE(1);
             // ---- Poisson (see mac_reg_kernel): rayleigh.py:412-456 / mixing.py:421-465 ----------------
             R *const pa = PA + opx, *const pb = PB + opx;
             auto tile_acc = [&](const R (&rs)[TI], const R (&dl)[TI], const R (&dr)[TI]) -> R {
@@ -1215,36 +1233,37 @@ __global__ void __launch_bounds__(T, 1) mac_big_kernel(const MacArgs<R> a)
                 return fma(cl, w_lef, fma(cr, w_rig, acc));
             };
             auto sweep = [&](R (&ph)[TI][TJ], const R *pi, R &wsum) -> R {
-                R hn[TJ], hs[TJ], hw[TI], he[TI];    // halo: rows i0-1 / i0+TI, columns j0-1 / j0+TJ
+                // in place, column by column; halo values are fetched where they are used (register budget)
+                R rs[TI], po_[TI], cl = R(0), cr = R(0);
 #pragma unroll
-                for (int k = 0; k < TJ; k++) { hn[k] = pi[-LDP + k]; hs[k] = pi[TI * LDP + k]; }
-#pragma unroll
-                for (int r = 0; r < TI; r++) { hw[r] = pi[r * LDP - 1]; he[r] = pi[r * LDP + TJ]; }
-                R rs[TI], dl[TI], dr[TI], po_[TI];
-#pragma unroll
-                for (int r = 0; r < TI; r++) { rs[r] = R(0); po_[r] = hw[r]; }
+                for (int r = 0; r < TI; r++) { rs[r] = R(0); po_[r] = pi[r * LDP - 1]; }
 #pragma unroll
                 for (int k = 0; k < TJ; k++) {
                     if (k < 5) wsum += __shfl_xor_sync(0xffffffffu, wsum, 16 >> k);
-                    R old[TI], nv[TI];
+                    const R hnk = pi[-LDP + k], hsk = pi[TI * LDP + k];
+                    R old[TI];
 #pragma unroll
                     for (int r = 0; r < TI; r++) old[r] = ph[r][k];
 #pragma unroll
                     for (int r = 0; r < TI; r++) {
-                        const R xm = (r > 0) ? old[r - 1] : hn[k], xp = (r < TI - 1) ? old[r + 1] : hs[k];
-                        const R ym = po_[r], yp = (k < TJ - 1) ? ph[r][k + 1] : he[r];
-                        nv[r] = fma(xp + xm, a.pk1, fma(yp + ym, a.pk2, cn[r][k]));
-                        const R d = nv[r] - old[r];
+                        const R xm = (r > 0) ? old[r - 1] : hnk, xp = (r < TI - 1) ? old[r + 1] : hsk;
+                        const R ym = po_[r], yp = (k < TJ - 1) ? ph[r][k + 1] : pi[r * LDP + TJ];
+                        const R nv = fma(xp + xm, a.pk1, fma(yp + ym, a.pk2, cn[r][k]));
+                        const R d = nv - old[r];
                         rs[r] = fma(d, d, rs[r]);
-                        if (k == 0) dl[r] = d;
-                        if (k == TJ - 1) dr[r] = d;
+                        if (k == 0) cl = fma(d, d, cl);
+                        if (k == TJ - 1) cr = fma(d, d, cr);
+                        ph[r][k] = nv;
+                        po_[r] = old[r];
                     }
-#pragma unroll
-                    for (int r = 0; r < TI; r++) { po_[r] = old[r]; ph[r][k] = nv[r]; }
                 }
 #pragma unroll
                 for (int st = TJ; st < 5; st++) wsum += __shfl_xor_sync(0xffffffffu, wsum, 16 >> st);
-                return tile_acc(rs, dl, dr);
+                R mid = R(0);
+#pragma unroll
+                for (int r = 1; r < TI - 1; r++) mid += rs[r];
+                const R acc = (TI > 1) ? fma(rs[0], w_top, fma(rs[TI - 1], w_bot, mid)) : rs[0] * (w_top + w_bot - R(1));
+                return fma(cl, w_lef, fma(cr, w_rig, acc));
             };
             auto commit = [&](const R (&nw)[TI][TJ], R *po) {
                 if (has_tile) {
@@ -1267,15 +1286,15 @@ __global__ void __launch_bounds__(T, 1) mac_big_kernel(const MacArgs<R> a)
                     }
                 }
             };
-            auto total = [&](const R *part) -> R {   // same pairwise order in every thread -> uniform decision
-                R q[NW];
+            auto total = [&](const R *part) -> R {   // fixed pairwise order in every thread -> uniform decision
+                R t4[NW / 4];
 #pragma unroll
-                for (int w = 0; w < NW; w++) q[w] = part[w];
+                for (int g = 0; g < NW / 4; g++) t4[g] = (part[4 * g] + part[4 * g + 1]) + (part[4 * g + 2] + part[4 * g + 3]);
 #pragma unroll
-                for (int st = 1; st < NW; st *= 2)
+                for (int st = 1; st < NW / 4; st *= 2)
 #pragma unroll
-                    for (int w = 0; w + st < NW; w += 2 * st) q[w] += q[w + st];
-                return q[0];
+                    for (int w = 0; w + st < NW / 4; w += 2 * st) t4[w] += t4[w + st];
+                return t4[0];
             };
             R accp;
             {   // sweep 1 starts from phi = 0: phi_1 = cn, no halo reads
@@ -1331,15 +1350,27 @@ __global__ void __launch_bounds__(T, 1) mac_big_kernel(const MacArgs<R> a)
             }
             TILE_LOOP { phi[r][k] = pf[r * LDP + k]; }     // the converged iterate (its ghosts are in the plane too)
             it_total += itp;
+            PHASE(2);
 
             // ---- p += phi (ghosts included, rayleigh.py:219 / mixing.py:188) and corrector (:461-464 / :470-473) ----
             if (has_tile) {
                 R *pp = p + o, *uu = u + o, *vv = v + o;
-                TILE_LOOP {
-                    const int e = r * LD + k;
-                    pp[e] += phi[r][k];
-                    if (r > 0 || !top) { const R pw = (r > 0) ? phi[r - 1][k] : pf[-LDP + k]; uu[e] = us[o + e] - dt * (phi[r][k] - pw) * inv_dx; }
-                    if (k > 0 || !lef) { const R ps = (k > 0) ? phi[r][k - 1] : pf[r * LDP - 1]; vv[e] = vs[o + e] - dt * (phi[r][k] - ps) * inv_dy; }
+#pragma unroll
+                for (int r0 = 0; r0 < TI; r0 += 2) {             // two tile rows at a time: their loads first (L2 latency once)
+                    R pold[2][TJ], uso[2][TJ], vso[2][TJ];
+#pragma unroll
+                    for (int rr = 0; rr < 2; rr++)
+#pragma unroll
+                        for (int k = 0; k < TJ; k++) { const int e = (r0 + rr) * LD + k; pold[rr][k] = pp[e]; uso[rr][k] = us[o + e]; vso[rr][k] = vs[o + e]; }
+#pragma unroll
+                    for (int rr = 0; rr < 2; rr++)
+#pragma unroll
+                        for (int k = 0; k < TJ; k++) {
+                            const int r = r0 + rr, e = r * LD + k;
+                            pp[e] = pold[rr][k] + phi[r][k];
+                            if (r > 0 || !top) { const R pw = (r > 0) ? phi[r - 1][k] : pf[-LDP + k]; uu[e] = uso[rr][k] - dt * (phi[r][k] - pw) * inv_dx; }
+                            if (k > 0 || !lef) { const R ps = (k > 0) ? phi[r][k - 1] : pf[r * LDP - 1]; vv[e] = vso[rr][k] - dt * (phi[r][k] - ps) * inv_dy; }
+                        }
                 }
                 if (top) {
 #pragma unroll
@@ -1359,6 +1390,7 @@ __global__ void __launch_bounds__(T, 1) mac_big_kernel(const MacArgs<R> a)
                 }
             }
             __syncthreads();
+            PHASE(3);
 
             // ---- transport: rayleigh.py:469-487 / mixing.py:478-495, in PASSES row blocks -------------
             {
@@ -1386,8 +1418,10 @@ __global__ void __launch_bounds__(T, 1) mac_big_kernel(const MacArgs<R> a)
                         }
                     }
                     __syncthreads();
+                    PHASE(4);
                     if (tid < 32) transport_wavefront3<R, NY>(0u, PLANE_B, 2 * PLANE_B, (ie - ib + 2) / 2, tid);
                     __syncthreads();
+                    PHASE(5);
                     if (mine) {
                         TILE_LOOP {
                             const int idx = (((i0 - ib + r) >> 1) * RS + j0 + k) * 2 + ((i0 - ib + r) & 1);
@@ -1395,6 +1429,7 @@ __global__ void __launch_bounds__(T, 1) mac_big_kernel(const MacArgs<R> a)
                         }
                     }
                     __syncthreads();
+                    PHASE(6);
                 }
             }
         }   // sub-steps
@@ -1445,6 +1480,8 @@ __global__ void __launch_bounds__(T, 1) mac_big_kernel(const MacArgs<R> a)
     }   // actions
 
     if (tid == 0) { a.stp[b] = stp; if (a.status) a.status[b] = status; }
+    if (DBG && dbg) { for (int n = 0; n < (DBG ? 8 : 1); n++) a.dbg[n] += (unsigned long long)tph[n]; }
+#undef PHASE
 #undef TILE_LOOP
 }
 
@@ -1457,7 +1494,7 @@ template <typename R> class MacEnv : public Env {
     void (*kernel)(const MacArgs<R>) = nullptr;
     int T = 0;
     size_t smem = 0;
-    bool reg_variant = false;
+    bool reg_variant = false, dbg_variant = false;
 
 public:
     MacEnv(const beacon_common &c, const beacon_mac_params &pp_, int kind_, const double *hu, const double *hv,
@@ -1491,10 +1528,12 @@ public:
             if (getenv("BEACON_MAC_DEBUG")) kernel = mac_reg_kernel<R, 50, 50, 2, 5, 256, true>;
             else kernel = mac_reg_kernel<R, 50, 50, 2, 5, 256, false>;
             T = 256; TI = 2; TJ = 5;
-            smem = sizeof(R) * (2 * 52 * 57 + 3 * 52 * 52); reg_variant = true;
+            smem = sizeof(R) * (2 * 52 * 57 + 3 * 52 * 52); reg_variant = true; dbg_variant = true;
         } else if (nx == 100 && ny == 100 && !getenv("BEACON_MAC_V1")) {
             // register-resident Poisson, fields in L2: one CTA of 500 tile threads per SM
-            kernel = mac_big_kernel<R, 100, 100, 4, 5, 512>; T = 512; TI = 4; TJ = 5;
+            if (getenv("BEACON_MAC_DEBUG")) kernel = mac_big_kernel<R, 100, 100, 4, 5, 512, true>;
+            else kernel = mac_big_kernel<R, 100, 100, 4, 5, 512, false>;
+            T = 512; TI = 4; TJ = 5; dbg_variant = true;
             smem = sizeof(R) * 2 * (size_t)102 * 105;
         } else if (2 * plane + 1024 <= 220 * 1024 && ((nx + 3) / 4) * ((ny + 4) / 5) <= 512) {
             kernel = mac_kernel<R, 4, 5, 512, false>; T = 512; TI = 4; TJ = 5; smem = 2 * plane;
@@ -1540,7 +1579,7 @@ public:
     {
         MacArgs<R> a = a_;
         static const bool debug = getenv("BEACON_MAC_DEBUG") != nullptr;
-        if (debug && reg_variant && a.mode == 0) {                       // tuning aid: cycles per phase of env 0
+        if (debug && dbg_variant && a.mode == 0) {                       // tuning aid: cycles per phase of env 0
             if (!dbgbuf.ptr) dbgbuf.alloc(8 * sizeof(unsigned long long));
             BEACON_CUDA_CHECK(cudaMemsetAsync(dbgbuf.ptr, 0, 64, st));
             a.dbg = dbgbuf.as<unsigned long long>();
@@ -1548,12 +1587,12 @@ public:
         kernel<<<a.B, T, smem, st>>>(a);
         BEACON_CUDA_CHECK(cudaGetLastError());
         launches++;
-        if (debug && reg_variant && a.mode == 0) {
+        if (debug && dbg_variant && a.mode == 0) {
             unsigned long long h[8];
             BEACON_CUDA_CHECK(cudaMemcpyAsync(h, dbgbuf.ptr, 64, cudaMemcpyDeviceToHost, st));
             BEACON_CUDA_CHECK(cudaStreamSynchronize(st));
-            fprintf(stderr, "[mac phases, env 0, cycles] bc %llu predictor %llu poisson %llu corrector %llu trcoef %llu wavefront %llu\n",
-                    h[0], h[1], h[2], h[3], h[4], h[5]);
+            fprintf(stderr, "[mac phases, env 0, cycles] bc %llu predictor %llu poisson %llu corrector %llu trcoef %llu wavefront %llu copyout %llu\n",
+                    h[0], h[1], h[2], h[3], h[4], h[5], h[6]);
         }
     }
     void reset(const ResetArgs &r) override
