@@ -40,7 +40,7 @@ def load_init_file(env, filename):
 @dataclass
 class ShkadovCfg:
     """shkadov.py:20-76."""
-    init: bool = True
+    init: object = True          # True: shipped init_field.dat, False: zeros (as the reference), "rest": h = q = 1
     L0: float = 150.0
     n_jets: int = 5
     jet_pos: float = 150.0
@@ -63,7 +63,10 @@ class ShkadovCfg:
                  n_interp=int(u_interp / dt), jet_pos=int(self.jet_pos / dx), jet_hw=int(jet_hw / dx),
                  jet_space=int(self.jet_space / dx), l_rwd=int(l_rwd / dx), n_obs=int(l_obs),
                  l_obs=int(l_obs / dx), obs_stride=int(1.0 / dx))   # :59-76, :246
-        if self.init:
+        d["x"] = np.linspace(0, nx, num=nx, endpoint=False) * dx    # :79
+        if isinstance(self.init, str) and self.init == "rest":      # reset_fields() state, :130-135 (init.py starts here)
+            d["h_init"], d["q_init"] = np.ones(nx), np.ones(nx)
+        elif self.init:
             f = init_fields()
             if nx > f["shkadov_h"].shape[0]:                        # same failure as load(), :366
                 raise ValueError(f"init field has {f['shkadov_h'].shape[0]} points, nx={nx} needs more "
@@ -118,8 +121,12 @@ class SloshingCfg:
         self.d.update(nx=nx, dx=float(self.L / nx), dt=dt, ndt_act=int(dt_act / dt), n_act=int(t_act / dt_act),
                       n_interp=int(u_interp / dt), obs_smpl=obs_smpl,
                       n_obs=nx // obs_smpl + (1 if (nx % obs_smpl != 0) else 0), h_max=1.0)
+        self.d.update(dt_act=dt_act, n_warmup=int(2.0 / dt_act),                                   # sloshing.py:27,47
+                      x=np.linspace(0, nx, num=nx, endpoint=False) * float(self.L / nx))           # :51
         h0, q0 = np.zeros(nx + 2), np.zeros(nx + 2)     # ghosts stay 0 until the first BC (sloshing.py:64-65)
-        if self.init:
+        if isinstance(self.init, str) and self.init == "rest":                                     # reset_fields(), :100-104
+            h0[:] = 1.0
+        elif self.init:
             f = init_fields()
             if f["sloshing_h"].shape[0] != nx:
                 raise ValueError("shipped sloshing init field has 200 cells (L=2.5)")
@@ -175,7 +182,8 @@ class RayleighCfg:
         self.d.update(nx=nx, ny=ny, dx=float(self.L / nx), dy=float(self.H / ny), dt=dt, pr=0.71, ra=self.ra,
                       Tc=-0.5, Th=0.5, C=0.75, ndt_act=int(dt_act / dt), n_act=int(t_act / dt_act),
                       nx_sgts=nx // self.n_sgts, nx_obs_pts=nxp, ny_obs_pts=nyp, n_obs_steps=4,
-                      nx_obs=nx // nxp, ny_obs=ny // nyp, n_obs_tot=3 * 4 * nxp * nyp, tol=1.0e-8, itmax=300000)
+                      nx_obs=nx // nxp, ny_obs=ny // nyp, n_obs_tot=3 * 4 * nxp * nyp, tol=1.0e-8, itmax=300000,
+                      n_warmup=int(200.0 / dt_act))                                                # rayleigh.py:35,51
         shape = (nx + 2, ny + 2)
         if self.init:
             f = init_fields()

@@ -341,10 +341,16 @@ def main():
         peak, peak_src = measured_peak()
         avg_launch_s = (total_ms / K) * 1e-3
         achieved = abytes * B / avg_launch_s / 1e9
+        # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed ncu capture of the
+        # same command (profiles/traffic.json, written from profiles/*_ncu_<env>.json); per-env traffic is
+        # launch-size independent (every env loads and stores its own state once), so a launch of another
+        # batch size is scaled by envs
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get(args.env)
+            t = json.load(open(tp)).get(args.env)
+            if t:
+                traffic = float(t["bytes_per_launch"]) * B / float(t["grid"])
         line = {
             "metric": "env-actions/sec", "value": value, "unit": "env-actions/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
