@@ -31,7 +31,7 @@ class BatchedEnv:
     get_state(name) / set_state(name, tensor)
     """
 
-    def __init__(self, name, batch, device=0, dtype=torch.float64, seed=0, env_index_base=0, **kwargs):
+    def __init__(self, name, batch, device=0, dtype=torch.float64, seed=0, env_index_base=0, init_state=None, **kwargs):
         if name not in CFG:
             raise ValueError(f"unknown env '{name}' (have {sorted(CFG)})")
         if not torch.cuda.is_available():
@@ -40,6 +40,15 @@ class BatchedEnv:
         self.device = torch.device("cuda", device)
         self.cfg = CFG[name](**kwargs)
         d = self.cfg.d
+        if init_state:                       # the reference's load(): fields that replace the shipped initial state
+            for k, v in init_state.items():
+                key = k + "_init"
+                if key not in d:
+                    raise ValueError(f"{name} has no initial field '{k}'")
+                v = np.ascontiguousarray(v, dtype=np.float64)
+                if v.shape != np.shape(d[key]):
+                    raise ValueError(f"init_state['{k}'] has shape {v.shape}, expected {np.shape(d[key])}")
+                d[key] = v
         self._lib = capi.lib()
         com = capi.Common(self.batch, device, capi.F64 if dtype == torch.float64 else capi.F32, 0, seed, env_index_base)
         h = C.c_void_p()

@@ -36,7 +36,9 @@ class _Single:
     _fields = ()
 
     def _make(self, seed=0, device=0, dtype=torch.float64, **kw):
-        self._env = BatchedEnv(self._name, batch=1, device=device, dtype=dtype, seed=seed, **kw)
+        self._made = dict(seed=seed, device=device, dtype=dtype, **kw)
+        self._env = BatchedEnv(self._name, batch=1, device=device, dtype=dtype, seed=seed,
+                               init_state=getattr(self, "_init_state", None), **kw)
         self.n_act = self._env.n_act
         self.stp = 0
         d = self._env.cfg.d
@@ -71,6 +73,45 @@ class _Single:
 
     def render(self, mode="human", show=False, dump=True):
         raise NotImplementedError("rendering is host-side visualisation, out of scope of the CUDA path (SURVEY.md §2)")
+
+    # ---- on-disk field files in the reference's text format (fieldio.py) -------------------------
+    def _dump_arrays(self):
+        d = self._env.cfg.d
+        if self._name in ("shkadov", "sloshing"):
+            return dict(x=d["x"], h=self.h, q=self.q)
+        return {k: getattr(self, k) for k in self._fields[:4]}
+
+    def _dump(self, field_name):
+        from . import fieldio
+        fieldio.dump_fields(self._name, field_name, **self._dump_arrays())
+
+    def load(self, filename):
+        """The reference's load(): the file's fields become the INITIAL state used by reset()
+        (shkadov.py:364-368, sloshing.py:310-314, rayleigh.py:356-362).  The native env is rebuilt."""
+        from . import fieldio
+        d = self._env.cfg.d
+        f = fieldio.load_fields(self._name, filename, nx=d["nx"] if self._name == "shkadov" else None)
+        f.pop("x", None)
+        self._init_state = f
+        self._rebuild()
+
+    def _rebuild(self):
+        self._env.close()
+        self._make(**self._made)
+
+    def warmup(self, n=None):
+        """Run `n` (default n_warmup) uncontrolled actions on the device, like the reference's
+        warmup() (shkadov.py:154-158, rayleigh.py:131-135, sloshing.py:125-129): the previous action is
+        repeated, observations and rewards are discarded."""
+        d = self._env.cfg.d
+        n = d["n_warmup"] if n is None else int(n)
+        e = self._env
+        a = e.get_state("u" if self._name in ("shkadov", "sloshing") else "a")
+        left = n
+        while left > 0:
+            k = min(50, left)
+            e.step_fused(a.reshape(1, 1, -1).expand(k, 1, -1).contiguous())
+            left -= k
 
     def close(self):
         self._env.close()
@@ -117,6 +158,13 @@ class shkadov(_Single):
         a = self._env.get_state("u") if u is None else torch.as_tensor(np.array(u, dtype=np.float64).reshape(1, -1))
         nz = None if noise is None else torch.as_tensor(np.array(noise, dtype=np.float64).reshape(1, -1))
         return self._finish(*self._env.step(a, noise=nz))
+
+
+    def dump(self, field_name, jet_name=None):
+        """shkadov.py:353-361: columns x, h, q; the current jet actions go to `jet_name`."""
+        self._dump(field_name)
+        if jet_name is not None:
+            np.savetxt(jet_name, self.u, fmt="%.5e")
 
 
 class shkadov_separable(shkadov):
@@ -193,6 +241,13 @@ class sloshing(_Single):
         return self._finish(*self._env.step(act))
 
 
+    def dump(self, field_name, control_name=None):
+        """sloshing.py:298-307: columns x, h, q (interior cells)."""
+        self._dump(field_name)
+        if control_name is not None:
+            np.savetxt(control_name, self.u, fmt="%.5e")
+
+
 class lorenz(_Single):
     """lorenz.py:18-172."""
     _name = "lorenz"
@@ -265,6 +320,14 @@ class rayleigh(_Mac):
         return self._finish(*self._env.step(act, want_iters=True))
 
 
+    def dump(self, field_name, act_name=None, nusselt_name=None):
+        """rayleigh.py:344-353: u, v, p, T stacked; the conditioned action goes to `act_name`.  The Nusselt
+        history the reference appends on the host every step (rayleigh.py:273) is not kept here."""
+        self._dump(field_name)
+        if act_name is not None:
+            np.savetxt(act_name, self.a, fmt="%.5e")
+
+
 class mixing(_Mac):
     """mixing.py:17-264."""
     _name = "mixing"
@@ -280,6 +343,14 @@ class mixing(_Mac):
     def step(self, a=None):
         self.a = self.a if a is None else int(a)
         return self._finish(*self._env.step(torch.tensor([self.a], dtype=torch.int32), want_iters=True))
+
+
+    def dump(self, field_name, action_name=None):
+        """mixing.py:362-373: u, v, p, C stacked; the action is appended to `action_name`."""
+        self._dump(field_name)
+        if action_name is not None:
+            with open(action_name, "a") as f:
+                f.write(str(self.a) + "\n")
 
 
 ENVS = {c.__name__: c for c in (shkadov, shkadov_separable, burgers, sloshing, lorenz, vortex, rayleigh, mixing)}
