@@ -345,12 +345,15 @@ def main():
         # same command (profiles/traffic.json, written from profiles/*_ncu_<env>.json); per-env traffic is
         # launch-size independent (every env loads and stores its own state once), so a launch of another
         # batch size is scaled by envs
-        traffic = None
+        traffic, secondary = None, None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             t = json.load(open(tp)).get(args.env)
             if t:
                 traffic = float(t["bytes_per_launch"]) * B / float(t["grid"])
+                if "fp64_pipe_active_pct" in t:     # the physical limiter of the fused kernels (same ncu capture)
+                    secondary = {"bound": "fp64 pipe (ncu sm__pipe_fp64_cycles_active, committed capture)",
+                                 "frac": t["fp64_pipe_active_pct"] / 100.0, "issue_slots_frac": t.get("issue_active_pct", 0) / 100.0}
         line = {
             "metric": "env-actions/sec", "value": value, "unit": "env-actions/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -362,7 +365,7 @@ def main():
                        **({"jacobi_sweeps_per_action": sweeps_per_action} if want_iters else {}),
                        **({"reset_seconds_random_warm_0_400": reset_s} if reset_s is not None else {})},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src,
+                         "traffic": traffic, "peak_source": peak_src, "secondary": secondary,
                          "model": "S-model algorithmic bytes (SURVEY.md §8d): %.0f B per env-action x %d envs per launch; "
                                   "sub-steps are fused on chip so DRAM traffic is far below this (F-model)" % (abytes, B)},
             "gpu_launches": int(launches),
