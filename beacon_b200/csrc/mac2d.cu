@@ -536,6 +536,8 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
     __shared__ R s_part[2][NW];
     __shared__ R s_seg[32];
     __shared__ R s_act[32];
+    __shared__ __align__(8) uint64_t s_mbar;
+    static_assert((N * sizeof(R)) % 16 == 0 && (NP * sizeof(R)) % 16 == 0, "bulk copies need 16-byte multiples");
     const int tid = threadIdx.x, b = blockIdx.x;
     const bool resetting = a.mode == 1;
     if (resetting && a.mask && !a.mask[b]) return;
@@ -577,7 +579,16 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
         if (tid == 0) a.stp[b] = 0;
         return;
     }
-    for (int e = tid; e < N; e += T) { U[e] = gu[e]; V[e] = gv[e]; S[e] = gs[e]; }
+    // state planes global -> shared: three bulk copies issued by one thread (TMA engine, no registers)
+    if (tid == 0) { mbar_init(&s_mbar, 1); fence_async_smem(); }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&s_mbar, 3u * (uint32_t)(N * sizeof(R)));
+        bulk_g2s(U, gu, (uint32_t)(N * sizeof(R)), &s_mbar);
+        bulk_g2s(V, gv, (uint32_t)(N * sizeof(R)), &s_mbar);
+        bulk_g2s(S, gs, (uint32_t)(N * sizeof(R)), &s_mbar);
+    }
+    mbar_wait(&s_mbar, 0);
     // Ghost cells of p only ever accumulate the same increments as their wall-adjacent cells (phi
     // ghosts are copies) and never feed back: they are brought up to date once, at the end of the
     // launch, from the launch-initial values of the adjacent cells saved in the `us` workspace plane.
@@ -947,8 +958,14 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
         }
     }   // actions
 
+    fence_async_smem();                                // my generic writes to U, V, S -> visible to the bulk engine
     __syncthreads();
-    for (int e = tid; e < N; e += T) { gu[e] = U[e]; gv[e] = V[e]; gs[e] = S[e]; }
+    if (tid == 0) {                                    // state planes shared -> global
+        bulk_s2g(gu, U, (uint32_t)(N * sizeof(R)));
+        bulk_s2g(gv, V, (uint32_t)(N * sizeof(R)));
+        bulk_s2g(gs, S, (uint32_t)(N * sizeof(R)));
+        bulk_commit_wait_all();
+    }
     if (has_tile && (top || bot || lef || rig)) {      // ghost cells of p += this launch's increments of the adjacent cell
         R *p = gp + o;
         const R *sv = a.us + row + o;
@@ -1043,6 +1060,7 @@ __global__ void __launch_bounds__(T, 1) mac_big_kernel(const MacArgs<R> a)
     static_assert(LANES_MAX <= 32 && 3 * (LANES_MAX * RS + 8) * 2 <= 2 * NP, "transport planes must fit the exchange planes");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(16) R s_part[2][NW];
+    __shared__ __align__(8) uint64_t s_mbar;
     __shared__ R s_red[NW];
     __shared__ R s_seg[128];
     __shared__ R s_act[128];
@@ -1095,6 +1113,8 @@ __global__ void __launch_bounds__(T, 1) mac_big_kernel(const MacArgs<R> a)
     int stp = a.stp[b];
     int status = 0;
     const R dt = a.dt, inv_dx = a.inv_dx, inv_dy = a.inv_dy;
+    if (tid == 0) { mbar_init(&s_mbar, 1); fence_async_smem(); }
+    uint32_t stage_phase = 0;
     const bool dbg = DBG && a.dbg != nullptr && b == 0 && tid == 0;
     long long tph[DBG ? 8 : 1] = {0}, tlast = dbg ? clock64() : 0;
 #define PHASE(n) do { if (DBG && dbg) { long long tn_ = clock64(); tph[n] += tn_ - tlast; tlast = tn_; } } while (0)
@@ -1162,14 +1182,19 @@ __global__ void __launch_bounds__(T, 1) mac_big_kernel(const MacArgs<R> a)
                     }
                 }
             }
-            __syncthreads();
             // stage u and v (ghosts included) in the exchange planes, free until the Poisson solve: the
-            // predictor reads ~15 neighbours per cell, from shared memory instead of L2
-            static_assert(N % 2 == 0, "vectorised staging");
-            for (int e = tid; e < N / 2; e += T) {
-                reinterpret_cast<typename vec2_of<R>::type *>(PA)[e] = reinterpret_cast<const typename vec2_of<R>::type *>(u)[e];
-                reinterpret_cast<typename vec2_of<R>::type *>(PB)[e] = reinterpret_cast<const typename vec2_of<R>::type *>(v)[e];
+            // predictor reads ~15 neighbours per cell, from shared memory instead of L2.  Two bulk copies
+            // (TMA engine) issued by one thread; everybody waits on the mbarrier.
+            static_assert((N * sizeof(R)) % 16 == 0, "bulk copies need 16-byte multiples");
+            fence_async_gmem(); fence_async_smem();    // my boundary writes / earlier plane accesses -> ordered before the bulk engine's
+            __syncthreads();
+            if (tid == 0) {
+                mbar_expect_tx(&s_mbar, 2u * (uint32_t)(N * sizeof(R)));
+                bulk_g2s(PA, u, (uint32_t)(N * sizeof(R)), &s_mbar);
+                bulk_g2s(PB, v, (uint32_t)(N * sizeof(R)), &s_mbar);
             }
+            mbar_wait(&s_mbar, stage_phase);
+            stage_phase ^= 1u;
             __syncthreads();
             PHASE(0);
 
