@@ -1071,7 +1071,14 @@ __global__ void __launch_bounds__(T, 1) mac_big_kernel(const MacArgs<R> a)
 
     R *PA = reinterpret_cast<R *>(smem_raw), *PB = PA + NP;
     const size_t row = (size_t)b * N;
-    R *u = a.u + row, *v = a.v + row, *p = a.p + row, *s = a.s + row, *us = a.us + row, *vs = a.vs + row;
+    R *u = a.u + row, *v = a.v + row, *p = a.p + row, *s = a.s + row;
+    // Thread-private copies of the tile of p, us, vs live in a per-env scratch laid out
+    // [field][cell][thread]: a thread's tile rows are 5 doubles at an odd offset in the planes (a warp
+    // access would touch 10 cache lines), in the scratch consecutive lanes are contiguous (2 lines),
+    // and the neighbour tile's cell is the same slot 1 / TILES_J threads away — equally coalesced.
+    constexpr int CELLS = TI * TJ;
+    R *sp = a.cc + (size_t)b * (3 * CELLS * T) + tid, *sus = sp + CELLS * T, *svs = sus + CELLS * T;
+#define SC(base, r, k) (base)[((r) * TJ + (k)) * T]
 
     const bool has_tile = tid < TILES;
     const int ti = tid / TILES_J, tj = tid - ti * TILES_J;
@@ -1091,7 +1098,6 @@ __global__ void __launch_bounds__(T, 1) mac_big_kernel(const MacArgs<R> a)
     if (resetting) {                                   // rayleigh.py:89-128, mixing.py:73-111
         for (int e = tid; e < N; e += T) {
             u[e] = ray ? a.u0[e] : R(0); v[e] = ray ? a.v0[e] : R(0); p[e] = ray ? a.p0[e] : R(0); s[e] = a.s0[e];
-            us[e] = R(0); vs[e] = R(0);
         }
         for (int e = tid; e < (ray ? a.n_sgts : 0); e += T) a.a_cur[(size_t)b * a.n_sgts + e] = R(0);
         R *hist = a.obs_hist + (size_t)b * a.n_obs;
@@ -1115,6 +1121,9 @@ __global__ void __launch_bounds__(T, 1) mac_big_kernel(const MacArgs<R> a)
     const R dt = a.dt, inv_dx = a.inv_dx, inv_dy = a.inv_dy;
     if (tid == 0) { mbar_init(&s_mbar, 1); fence_async_smem(); }
     uint32_t stage_phase = 0;
+    // pressure: the scratch copy is authoritative during the launch; the plane keeps the launch-initial
+    // values until the end (needed for the ghost cells, see there)
+    if (has_tile) { TILE_LOOP { SC(sp, r, k) = p[o + r * LD + k]; } }
     const bool dbg = DBG && a.dbg != nullptr && b == 0 && tid == 0;
     long long tph[DBG ? 8 : 1] = {0}, tlast = dbg ? clock64() : 0;
 #define PHASE(n) do { if (DBG && dbg) { long long tn_ = clock64(); tph[n] += tn_ - tlast; tlast = tn_; } } while (0)
@@ -1203,10 +1212,16 @@ __global__ void __launch_bounds__(T, 1) mac_big_kernel(const MacArgs<R> a)
             {
             R usr[TI][TJ], vsr[TI][TJ];
             if (has_tile) {
-                const R *uu = PA + o, *vv = PB + o, *sc = s + o, *pp = p + o;
+                const R *uu = PA + o, *vv = PB + o, *sc = s + o;
+                R pt[TI][TJ], pwh[TJ], psh[TI];    // my pressure tile, the last row of the tile above, the last column of the left tile
+                TILE_LOOP { pt[r][k] = SC(sp, r, k); }
+#pragma unroll
+                for (int k = 0; k < TJ; k++) pwh[k] = top ? R(0) : SC(sp - TILES_J, TI - 1, k);
+#pragma unroll
+                for (int r = 0; r < TI; r++) psh[r] = lef ? R(0) : SC(sp - 1, r, TJ - 1);
                 TILE_LOOP {
                     const int e = r * LD + k;
-                    const R uc = uu[e], vc = vv[e], pc = pp[e];
+                    const R uc = uu[e], vc = vv[e], pc = pt[r][k];
                     usr[r][k] = R(0); vsr[r][k] = R(0);
                     if (r > 0 || !top) {               // i >= 2
                         R uE = R(0.5) * (uu[e + LD] + uc), uW = R(0.5) * (uc + uu[e - LD]);
@@ -1214,9 +1229,8 @@ __global__ void __launch_bounds__(T, 1) mac_big_kernel(const MacArgs<R> a)
                         R vN = R(0.5) * (vv[e + 1] + vv[e - LD + 1]), vS = R(0.5) * (vc + vv[e - LD]);
                         R conv = (uE * uE - uW * uW) * inv_dx + (uN * vN - uS * vS) * inv_dy;
                         R diff = ((uu[e + LD] - R(2) * uc + uu[e - LD]) * a.inv_dx2 + (uu[e + 1] - R(2) * uc + uu[e - 1]) * a.inv_dy2) * a.dcoef;
-                        R pres = (pc - pp[e - LD]) * inv_dx;
+                        R pres = (pc - ((r > 0) ? pt[r - 1][k] : pwh[k])) * inv_dx;
                         usr[r][k] = uc + dt * (diff - conv - pres);
-                        us[o + e] = usr[r][k];
                     }
                     if (k > 0 || !lef) {               // j >= 2
                         R vE = R(0.5) * (vv[e + LD] + vc), vW = R(0.5) * (vc + vv[e - LD]);
@@ -1224,21 +1238,21 @@ __global__ void __launch_bounds__(T, 1) mac_big_kernel(const MacArgs<R> a)
                         R vN = R(0.5) * (vv[e + 1] + vc), vS = R(0.5) * (vc + vv[e - 1]);
                         R conv = (uE * vE - uW * vW) * inv_dx + (vN * vN - vS * vS) * inv_dy;
                         R diff = ((vv[e + LD] - R(2) * vc + vv[e - LD]) * a.inv_dx2 + (vv[e + 1] - R(2) * vc + vv[e - 1]) * a.inv_dy2) * a.dcoef;
-                        R pres = (pc - pp[e - 1]) * inv_dy;
+                        R pres = (pc - ((k > 0) ? pt[r][k - 1] : psh[r])) * inv_dy;
                         R rhs = diff - conv - pres;
                         if (ray) rhs += sc[e];
                         vsr[r][k] = vc + dt * rhs;
-                        vs[o + e] = vsr[r][k];
                     }
                 }
+                TILE_LOOP { SC(sus, r, k) = usr[r][k]; SC(svs, r, k) = vsr[r][k]; }   // walls: 0 (i = 1 / j = 1)
             }
             __syncthreads();                       // us, vs of the neighbouring tiles are visible
             // Poisson right-hand side cn = -div(us, vs)/dt dx2 dy2 / (2 (dx2 + dy2)); phi_1 = cn
             TILE_LOOP {
                 R cv = R(0);
                 if (has_tile) {
-                    const R ue = (r < TI - 1) ? usr[r + 1][k] : us[o + (r + 1) * LD + k];
-                    const R vn = (k < TJ - 1) ? vsr[r][k + 1] : vs[o + r * LD + k + 1];
+                    const R ue = (r < TI - 1) ? usr[r + 1][k] : (bot ? R(0) : SC(sus + TILES_J, 0, k));     // us(NX+1, j) = 0
+                    const R vn = (k < TJ - 1) ? vsr[r][k + 1] : (rig ? R(0) : SC(svs + 1, r, 0));           // vs(i, NY+1) = 0
                     cv = -(((ue - usr[r][k]) * inv_dx + (vn - vsr[r][k]) * inv_dy) * a.cscale) * a.inv_den;
                 }
                 cn[r][k] = cv; phi[r][k] = cv;
@@ -1377,41 +1391,25 @@ __global__ void __launch_bounds__(T, 1) mac_big_kernel(const MacArgs<R> a)
             it_total += itp;
             PHASE(2);
 
-            // ---- p += phi (ghosts included, rayleigh.py:219 / mixing.py:188) and corrector (:461-464 / :470-473) ----
+            // ---- p += phi (rayleigh.py:219 / mixing.py:188; ghost cells: end of the launch) and corrector (:461-464 / :470-473) ----
             if (has_tile) {
-                R *pp = p + o, *uu = u + o, *vv = v + o;
+                R *uu = u + o, *vv = v + o;
 #pragma unroll
-                for (int r0 = 0; r0 < TI; r0 += 2) {             // two tile rows at a time: their loads first (L2 latency once)
+                for (int r0 = 0; r0 < TI; r0 += 2) {             // two tile rows at a time: their loads first
                     R pold[2][TJ], uso[2][TJ], vso[2][TJ];
 #pragma unroll
                     for (int rr = 0; rr < 2; rr++)
 #pragma unroll
-                        for (int k = 0; k < TJ; k++) { const int e = (r0 + rr) * LD + k; pold[rr][k] = pp[e]; uso[rr][k] = us[o + e]; vso[rr][k] = vs[o + e]; }
+                        for (int k = 0; k < TJ; k++) { pold[rr][k] = SC(sp, r0 + rr, k); uso[rr][k] = SC(sus, r0 + rr, k); vso[rr][k] = SC(svs, r0 + rr, k); }
 #pragma unroll
                     for (int rr = 0; rr < 2; rr++)
 #pragma unroll
                         for (int k = 0; k < TJ; k++) {
                             const int r = r0 + rr, e = r * LD + k;
-                            pp[e] = pold[rr][k] + phi[r][k];
+                            SC(sp, r, k) = pold[rr][k] + phi[r][k];
                             if (r > 0 || !top) { const R pw = (r > 0) ? phi[r - 1][k] : pf[-LDP + k]; uu[e] = uso[rr][k] - dt * (phi[r][k] - pw) * inv_dx; }
                             if (k > 0 || !lef) { const R ps = (k > 0) ? phi[r][k - 1] : pf[r * LDP - 1]; vv[e] = vso[rr][k] - dt * (phi[r][k] - ps) * inv_dy; }
                         }
-                }
-                if (top) {
-#pragma unroll
-                    for (int k = 0; k < TJ; k++) pp[-LD + k] += phi[0][k];
-                }
-                if (bot) {
-#pragma unroll
-                    for (int k = 0; k < TJ; k++) pp[TI * LD + k] += phi[TI - 1][k];
-                }
-                if (lef) {
-#pragma unroll
-                    for (int r = 0; r < TI; r++) pp[r * LD - 1] += phi[r][0];
-                }
-                if (rig && ray) {                       // mixing: the j = NY+1 ghost of phi is 0
-#pragma unroll
-                    for (int r = 0; r < TI; r++) pp[r * LD + TJ] += phi[r][TJ - 1];
                 }
             }
             __syncthreads();
@@ -1504,9 +1502,33 @@ __global__ void __launch_bounds__(T, 1) mac_big_kernel(const MacArgs<R> a)
         }
     }   // actions
 
+    // pressure back to its plane.  Ghost cells of p accumulate the same increments as their wall-
+    // adjacent cells (phi ghosts are copies; mixing's j = NY+1 ghost of phi is 0) and never feed back:
+    // ghost += adjacent(final) - adjacent(launch start, still in the plane).
+    if (has_tile) {
+        R *pp = p + o;
+        if (top) {
+#pragma unroll
+            for (int k = 0; k < TJ; k++) pp[-LD + k] += SC(sp, 0, k) - pp[k];
+        }
+        if (bot) {
+#pragma unroll
+            for (int k = 0; k < TJ; k++) pp[TI * LD + k] += SC(sp, TI - 1, k) - pp[(TI - 1) * LD + k];
+        }
+        if (lef) {
+#pragma unroll
+            for (int r = 0; r < TI; r++) pp[r * LD - 1] += SC(sp, r, 0) - pp[r * LD];
+        }
+        if (rig && ray) {
+#pragma unroll
+            for (int r = 0; r < TI; r++) pp[r * LD + TJ] += SC(sp, r, TJ - 1) - pp[r * LD + TJ - 1];
+        }
+        TILE_LOOP { pp[r * LD + k] = SC(sp, r, k); }
+    }
     if (tid == 0) { a.stp[b] = stp; if (a.status) a.status[b] = status; }
     if (DBG && dbg) { for (int n = 0; n < (DBG ? 8 : 1); n++) a.dbg[n] += (unsigned long long)tph[n]; }
 #undef PHASE
+#undef SC
 #undef TILE_LOOP
 }
 
@@ -1519,7 +1541,7 @@ template <typename R> class MacEnv : public Env {
     void (*kernel)(const MacArgs<R>) = nullptr;
     int T = 0;
     size_t smem = 0;
-    bool reg_variant = false, dbg_variant = false;
+    bool reg_variant = false, dbg_variant = false, big_variant = false;
 
 public:
     MacEnv(const beacon_common &c, const beacon_mac_params &pp_, int kind_, const double *hu, const double *hv,
@@ -1558,7 +1580,7 @@ public:
             // register-resident Poisson, fields in L2: one CTA of 500 tile threads per SM
             if (getenv("BEACON_MAC_DEBUG")) kernel = mac_big_kernel<R, 100, 100, 4, 5, 512, true>;
             else kernel = mac_big_kernel<R, 100, 100, 4, 5, 512, false>;
-            T = 512; TI = 4; TJ = 5; dbg_variant = true;
+            T = 512; TI = 4; TJ = 5; dbg_variant = true; big_variant = true;
             smem = sizeof(R) * 2 * (size_t)102 * 105;
         } else if (2 * plane + 1024 <= 220 * 1024 && ((nx + 3) / 4) * ((ny + 4) / 5) <= 512) {
             kernel = mac_kernel<R, 4, 5, 512, false>; T = 512; TI = 4; TJ = 5; smem = 2 * plane;
@@ -1577,7 +1599,8 @@ public:
         if (ray) { upload_as<R>(u0, hu, n); upload_as<R>(v0, hv, n); upload_as<R>(p0, hp, n); }
         upload_as<R>(s0, hs, n);
         add_field("u", u.ptr, n); add_field("v", v.ptr, n); add_field("p", pp.ptr, n); add_field(ray ? "T" : "C", s.ptr, n);
-        if (!reg_variant) { add_field("us", us.ptr, n); add_field("vs", vs.ptr, n); }
+        if (!reg_variant && !big_variant) { add_field("us", us.ptr, n); add_field("vs", vs.ptr, n); }
+        if (big_variant) cc.alloc((size_t)B * 3 * 20 * 512 * sizeof(R));     // [B][p, us, vs][cell][thread] tile scratch
         if (ray) add_field("a", a_cur.ptr, p.n_sgts); else add_field("a", a_int.ptr, 1, true);
         add_field("obs", obs_hist.ptr, info.n_obs); add_field("stp", stp.ptr, 1, true);
 
@@ -1596,7 +1619,7 @@ public:
         a.tcoef = (R)(ray ? 1.0 / std::sqrt(p.pr * p.ra) : 1.0 / p.pe);
         a.Tc = (R)p.Tc; a.Th = (R)p.Th; a.Cmax = (R)p.C; a.u_max = (R)p.u_max; a.ref_c = (R)p.ref_c; a.tol = (R)p.tol;
         a.B = B;
-        a.u = u.as<R>(); a.v = v.as<R>(); a.p = pp.as<R>(); a.s = s.as<R>(); a.us = us.as<R>(); a.vs = vs.as<R>();
+        a.u = u.as<R>(); a.v = v.as<R>(); a.p = pp.as<R>(); a.s = s.as<R>(); a.us = us.as<R>(); a.vs = vs.as<R>(); a.cc = cc.as<R>();
         a.a_cur = a_cur.as<R>(); a.a_int = a_int.as<int32_t>(); a.obs_hist = obs_hist.as<R>(); a.stp = stp.as<int32_t>();
         a.u0 = u0.as<R>(); a.v0 = v0.as<R>(); a.p0 = p0.as<R>(); a.s0 = s0.as<R>();
     }
