@@ -1046,8 +1046,8 @@ __device__ __noinline__ void transport_wavefront3(uint32_t offA, uint32_t offW, 
 // L2-resident global memory (Poisson is > 90 % of the work: ~65 sweeps per sub-step), transport in
 // row passes through the three-plane wavefront above.  One CTA per SM.
 // ---------------------------------------------------------------------------------------
-template <typename R, int NX, int NY, int TI, int TJ, int T, bool DBG>
-__global__ void __launch_bounds__(T, 1) mac_big_kernel(const MacArgs<R> a)
+template <typename R, int NX, int NY, int TI, int TJ, int T, int MINB, bool DBG>
+__global__ void __launch_bounds__(T, MINB) mac_big_kernel(const MacArgs<R> a)
 {
     constexpr int LD = NY + 2, N = (NX + 2) * LD;
     constexpr int LDP = ((LD + 6) / 8) * 8 + 1;         // exchange planes: stride = 1 mod 8
@@ -1578,8 +1578,8 @@ public:
             smem = sizeof(R) * (2 * 52 * 57 + 3 * 52 * 52); reg_variant = true; dbg_variant = true;
         } else if (nx == 100 && ny == 100 && !getenv("BEACON_MAC_V1")) {
             // register-resident Poisson, fields in L2: one CTA of 500 tile threads per SM
-            if (getenv("BEACON_MAC_DEBUG")) kernel = mac_big_kernel<R, 100, 100, 4, 5, 512, true>;
-            else kernel = mac_big_kernel<R, 100, 100, 4, 5, 512, false>;
+            if (getenv("BEACON_MAC_DEBUG")) kernel = mac_big_kernel<R, 100, 100, 4, 5, 512, 1, true>;
+            else kernel = mac_big_kernel<R, 100, 100, 4, 5, 512, 1, false>;
             T = 512; TI = 4; TJ = 5; dbg_variant = true; big_variant = true;
             smem = sizeof(R) * 2 * (size_t)102 * 105;
         } else if (2 * plane + 1024 <= 220 * 1024 && ((nx + 3) / 4) * ((ny + 4) / 5) <= 512) {
@@ -1600,7 +1600,7 @@ public:
         upload_as<R>(s0, hs, n);
         add_field("u", u.ptr, n); add_field("v", v.ptr, n); add_field("p", pp.ptr, n); add_field(ray ? "T" : "C", s.ptr, n);
         if (!reg_variant && !big_variant) { add_field("us", us.ptr, n); add_field("vs", vs.ptr, n); }
-        if (big_variant) cc.alloc((size_t)B * 3 * 20 * 512 * sizeof(R));     // [B][p, us, vs][cell][thread] tile scratch
+        if (big_variant) cc.alloc((size_t)B * 3 * TI * TJ * T * sizeof(R));  // [B][p, us, vs][cell][thread] tile scratch
         if (ray) add_field("a", a_cur.ptr, p.n_sgts); else add_field("a", a_int.ptr, 1, true);
         add_field("obs", obs_hist.ptr, info.n_obs); add_field("stp", stp.ptr, 1, true);
 
