@@ -579,6 +579,7 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
         if (tid == 0) a.stp[b] = 0;
         return;
     }
+    for (int e = tid; e < 2 * NP; e += T) PA[e] = R(0);   // masked wavefront steps read padding slots: keep them finite
     // state planes global -> shared: three bulk copies issued by one thread (TMA engine, no registers)
     if (tid == 0) { mbar_init(&s_mbar, 1); fence_async_smem(); }
     __syncthreads();
@@ -1119,6 +1120,10 @@ __global__ void __launch_bounds__(T, MINB) mac_big_kernel(const MacArgs<R> a)
     int stp = a.stp[b];
     int status = 0;
     const R dt = a.dt, inv_dx = a.inv_dx, inv_dy = a.inv_dy;
+    // The uniform transport wavefront reads a few never-written padding slots of the planes during its
+    // masked steps; their values cannot reach a result as long as they are finite (they are multiplied
+    // by the zero B_S of column 1), so the planes must not start with stale NaN bit patterns.
+    for (int e = tid; e < 2 * NP; e += T) PA[e] = R(0);
     if (tid == 0) { mbar_init(&s_mbar, 1); fence_async_smem(); }
     uint32_t stage_phase = 0;
     // pressure: the scratch copy is authoritative during the launch; the plane keeps the launch-initial
