@@ -472,7 +472,10 @@ __device__ __noinline__ void transport_wavefront_f64(uint32_t sAA, uint32_t sWW,
     double w0 = w1c.x, w1 = w1c.y;
     // bases biased by -lane: element [t] is column t - l + 2 (coefficients) / t - l + 1 (store)
     const uint32_t aA = sAA + rowA + (uint32_t)(2 - l) * 16u, aW = sWW + rowA + (uint32_t)(2 - l) * 16u;
-    const uint32_t aV = sV + rowV + (uint32_t)(2 - l) * 8u, aS = sS + rowV + (uint32_t)(1 - l) * 8u;
+    const uint32_t aV = sV + rowV + (uint32_t)(2 - l) * 8u;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // store pointers: S plane rows 2l+1, 2l+2, biased so that element [t] is column t - l + 1
+    double *S0o = reinterpret_cast<double *>(smem_raw + (sS - (uint32_t)__cvta_generic_to_shared(smem_raw)) + rowV) + (1 - l), *S1o = S0o + LD;
     double2 an = lds128_f64(aA), wn = lds128_f64(aW);
     double v0n = lds64_f64(aV), v1n = lds64_f64(aV + LD * 8u);
     double last_new = 0.0;
@@ -494,11 +497,14 @@ __device__ __noinline__ void transport_wavefront_f64(uint32_t sAA, uint32_t sWW,
         const double n0 = fma(w0, wv, p0);
         const double n1 = fma(w1, n0, p1);
         last_new = n1;
-        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.shared.f64 [%3], %4;\n\t@q st.shared.f64 [%3+%10], %5;\n\t"
-                     "@q fma.rn.f64 %0, %6, %4, %8;\n\t@q fma.rn.f64 %1, %7, %5, %9;\n\t}"
-                     : "+d"(p0), "+d"(p1)
-                     : "r"(act_), "r"(aS + (uint32_t)t * 8u), "d"(n0), "d"(n1), "d"(s0n), "d"(s1n), "d"(an.x), "d"(an.y), "n"(LD * 8)
-                     : "memory");
+        // plain C++ stores (the coefficient loads above are plain asm that never aliases them, so the
+        // compiler hoists the loads over the stores: with an ordered asm store every load waited for the
+        // previous step's store and its latency sat in the dependent chain — 81 -> 48 cycles per step
+        // in isolation, tools/micro/wave.cu)
+        if (act_) {
+            S0o[t] = n0; S1o[t] = n1;
+            p0 = fma(s0n, n0, an.x); p1 = fma(s1n, n1, an.y);
+        }
         w0 = wn.x; w1 = wn.y;
         an = an2; wn = wn2; v0n = v0n2; v1n = v1n2;
     }
