@@ -6,6 +6,8 @@
 // One CTA per environment; each thread keeps C consecutive points of u, up, upp in registers
 // for all ndt_act sub-steps of all fused actions (same scheme as shkadov.cu): per sub-step only
 // the chunk edges (first u, last two u) cross shared memory, one __syncthreads per sub-step.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace beacon {
@@ -95,7 +97,7 @@ __global__ void __launch_bounds__(T) burgers_kernel(const BurArgs<R> a)
                 R du = (F[m + 1] - F[m]) * a.inv_dx;
                 R rhs = u[m] * du;                                                       // rhs(), :253-255
                 if (i == a.ctrl_pos) rhs += forcing;                                     // :149
-                if (i >= 1 && i <= nx - 2) u[m] = (R(4) * up[m] - upp[m] - a.two_dt * rhs) / R(3);   // dert(), :247-249
+                if (i >= 1 && i <= nx - 2) u[m] = fdiv(R(4) * up[m] - upp[m] - a.two_dt * rhs, R(3));   // dert(), :247-249
             }
         }
         // ---- obs / reward ------------------------------------------------------------------
@@ -139,7 +141,11 @@ template <typename R> class BurgersEnv : public Env {
     beacon_burgers_params p;
     DeviceBuffer u, up, upp, a_cur, stp, draws;
     BurArgs<R> base{};
-    static constexpr int C = 4, T = 128;
+    // two variants: 4 points per thread (throughput, large batches) and 2 points per thread with
+    // twice the warps (latency of a single env: configs[0] steps ONE env, the per-sub-step
+    // dependent chain is what counts)
+    int C = 4, T = 128;
+    void (*kernel)(const BurArgs<R>) = nullptr;
 
 public:
     BurgersEnv(const beacon_common &c, const beacon_burgers_params &pp) : p(pp)
@@ -147,7 +153,9 @@ public:
         common = c;
         const int B = c.batch, nx = p.nx;
         BEACON_REQUIRE(nx >= 8 && p.ndt_act > 0, "burgers: bad sizes");
-        if (nx > C * T - 1) throw Error(BEACON_ERR_UNSUPPORTED, "burgers: nx > 511 not supported");
+        if (nx > 511) throw Error(BEACON_ERR_UNSUPPORTED, "burgers: nx > 511 not supported");
+        if (B <= 296 && !getenv("BEACON_BURGERS_C4")) { C = 2; T = 256; kernel = burgers_kernel<R, 2, 256>; }
+        else { C = 4; T = 128; kernel = burgers_kernel<R, 4, 128>; }
         BEACON_REQUIRE(p.ctrl_pos - p.n_obs_pts >= 0 && p.ctrl_pos >= 1 && p.ctrl_pos <= nx - 2, "burgers: control point outside the domain");
         info.kind = BEACON_BURGERS; info.batch = B; info.dtype = real_traits<R>::dtype; info.device = c.device;
         info.n_obs = p.n_obs_pts; info.act_dim = 1; info.act_is_int = 0; info.rwd_dim = 1; info.n_act = p.n_act; info.noise_dim = 1;
@@ -168,7 +176,7 @@ public:
         BEACON_REQUIRE(r.obs != nullptr, "reset: obs must not be NULL");
         BurArgs<R> a = base;
         a.mode = 1; a.mask = r.mask; a.obs = (R *)r.obs;
-        burgers_kernel<R, C, T><<<a.B, T, 0, r.stream>>>(a);
+        kernel<<<a.B, T, 0, r.stream>>>(a);
         BEACON_CUDA_CHECK(cudaGetLastError());
         launches++;
     }
@@ -177,7 +185,7 @@ public:
         BurArgs<R> a = base;
         a.mode = 0; a.n_fused = s.n_fused; a.actions = (const R *)s.actions; a.noise = (const R *)s.noise;
         a.obs = (R *)s.obs; a.rwd = (R *)s.rwd; a.done = s.done; a.trunc = s.trunc; a.status = s.status;
-        burgers_kernel<R, C, T><<<a.B, T, 0, s.stream>>>(a);
+        kernel<<<a.B, T, 0, s.stream>>>(a);
         BEACON_CUDA_CHECK(cudaGetLastError());
         launches++;
     }
