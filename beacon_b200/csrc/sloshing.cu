@@ -29,9 +29,12 @@ __global__ void __launch_bounds__(T) sloshing_kernel(const SloArgs<R> a)
     __shared__ R ex[2][8][T];
     __shared__ R s_q[C * T];
     __shared__ R s_red[T / 32];
+    __shared__ R s_alpha[256];                              // min(i / n_interp, 1): one IEEE division per entry, once per launch
     const int tid = threadIdx.x, b = blockIdx.x, nx = a.nx, n2 = a.n2;
     const bool resetting = a.mode == 1;
     if (resetting && a.mask && !a.mask[b]) return;
+    for (int i = tid; i < a.ndt_act && i < 256; i += T) s_alpha[i] = (R)fmin((double)i / (double)a.n_interp, 1.0);
+    __syncthreads();
     const int a0 = tid * C - a.off;
     const int tl = tid > 0 ? tid - 1 : 0, tr = tid < T - 1 ? tid + 1 : T - 1;
     const size_t row = (size_t)b * n2;
@@ -87,7 +90,7 @@ __global__ void __launch_bounds__(T) sloshing_kernel(const SloArgs<R> a)
                 fh[m] = R(0.5) * (eq[m] + eq[m + 1]) - (R(0.5) * c) * (eh[m + 1] - eh[m]);
                 fq[m] = R(0.5) * (ew[m] + ew[m + 1]) - (R(0.5) * c) * (eq[m + 1] - eq[m]);
             }
-            R alpha = (R)fmin((double)it / (double)a.n_interp, 1.0);                     // :218-220
+            R alpha = it < 256 ? s_alpha[it] : (R)fmin((double)it / (double)a.n_interp, 1.0);   // :218-220
             R f = ((R(1) - alpha) * uprev + alpha * ucur) * a.amp;
 #pragma unroll
             for (int m = 0; m < C; m++) {
