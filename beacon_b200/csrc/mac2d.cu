@@ -9,22 +9,25 @@
 // get_obs :237-256, get_rwd :259-264.
 //
 // B200 design: ONE CTA PER ENVIRONMENT runs every sub-step of every fused action without
-// returning to the host.
-//   * each thread owns a TI x TJ tile of cells (TJ contiguous in y); the Poisson right-hand side
-//     of its tile stays in REGISTERS for the whole solve, phi ping-pongs between two
-//     shared-memory planes, so a Jacobi sweep is: halo loads, ~9 flops per cell, one store,
-//     a warp-shuffle residual reduction and ONE __syncthreads; all threads evaluate the same
-//     residual sum in the same order, so the data-dependent `while err > tol` is uniform;
+// returning to the host.  Three kernels:
+//   * mac_reg_kernel  — rayleigh 50x50: phi and the Poisson right-hand side of a 2x5 tile in
+//     REGISTERS, in-place Jacobi sweeps over two strided exchange planes (one barrier per sweep),
+//     convergence test two sweeps behind and interleaved with the next sweep (exact sweep counts),
+//     u, v, T planes in shared memory (TMA bulk loads / stores), 2 CTAs per SM;
+//   * mac_big_kernel  — mixing 100x100: the same register-resident Poisson with 4x5 tiles, field
+//     planes in L2/HBM, tile copies of p, us, vs in a thread-interleaved scratch, u / v staged in
+//     the exchange planes for the predictor (TMA bulk copies), transport in two row passes;
+//   * mac_kernel      — generic fallback for any other grid up to ~100x100 cells: phi ping-pongs
+//     between two shared-memory planes, right-hand side in registers, fields in global memory.
+// Common to all:
 //   * the residual reproduces the reference's: sum over the whole ghost-inclusive array after
 //     the ghost update (ghost copies re-count the wall-adjacent cells; mixing's top ghost is 0);
+//     all threads evaluate the same sum in the same order, so `while err > tol` is uniform;
 //   * the in-place lexicographic transport sweep (a Gauss-Seidel-like dependence on the new
 //     west/south neighbours) is split in two: all threads pre-compute, per cell, the part of the
-//     update that only involves OLD values plus the two coefficients multiplying the new
-//     neighbours; then one warp runs the remaining 2-FMA recurrence as a skewed wavefront, rows
-//     across lanes, the new west value travelling by warp shuffle (no barriers);
-//   * rayleigh (50x50): all eight planes live in shared memory (173 KB fp64); mixing (100x100,
-//     83 KB per plane): phi planes in shared memory, the other planes stay in L2-resident global
-//     memory (Poisson dominates: ~21 k sweeps per action vs 250 predictor/transport passes).
+//     update that only involves OLD values plus the coefficients multiplying the new neighbours;
+//     then one warp runs the remaining 2-FMA recurrence as a skewed wavefront, rows across lanes,
+//     the new west value travelling by warp shuffle (no barriers).
 #include <cstdio>
 #include <cstdlib>
 #include <type_traits>

@@ -355,3 +355,34 @@ def test_capi_errors_are_reported():
         env.step(torch.zeros(3, dtype=torch.int32))
     with pytest.raises(KeyError):
         env.get_state("nope")
+
+
+# ----------------------------------------------------------------------------- generic 2D kernel (non-default grids)
+def test_generic_mac_kernel(monkeypatch, golden):
+    """Grids other than the two reference defaults take the generic one-CTA-per-env kernel (phi planes
+    in shared memory, fields in global memory): rayleigh from rest on a 100x50 cell against the oracle,
+    and — forced with BEACON_MAC_V1 — the reference's mixing golden step; sweep counts exact."""
+    env = make("rayleigh", 2, init=False, L=2.0, H=1.0, n_sgts=5)
+    o = bo.rayleigh(init=False, L=2.0, H=1.0, n_sgts=5)
+    env.reset(); o.reset()
+    assert env.cfg.d["nx"] == 100 and env.cfg.d["ny"] == 50
+    rng = np.random.default_rng(31)
+    for k in range(2):
+        a = rng.uniform(-1, 1, 5)
+        obs, rwd, d, t = env.step(torch.as_tensor(np.stack([a, a])), want_iters=True)
+        ro = o.step(a)
+        assert int(env.last_iters[0, 1]) == int(o.last_iters.sum())
+        for f in ("u", "v", "p", "T"):
+            close(env.get_state(f)[0], getattr(o, f).reshape(-1), what=f"rayleigh 100x50 {f}")
+        close(obs[0], ro[0], what="obs")
+        close(rwd[1:], np.array([ro[1]]), rtol=1e-12, what="rwd")
+    assert int(env.status.max()) == 0
+    monkeypatch.setenv("BEACON_MAC_V1", "1")
+    g = golden("mixing")
+    env = make("mixing", 1)
+    env.reset()
+    obs, rwd, d, t = env.step(torch.tensor([int(g["actions"][0])], dtype=torch.int32), want_iters=True)
+    assert int(env.last_iters[0, 0]) == int(g["itp"][0].sum())
+    for f in ("u", "v", "p", "C"):
+        close(env.get_state(f)[0], g[f][0].reshape(-1), what=f"mixing generic {f}")
+    assert "us" in env.fields          # the generic kernel keeps the starred velocities as state fields
