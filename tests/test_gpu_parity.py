@@ -386,3 +386,33 @@ def test_generic_mac_kernel(monkeypatch, golden):
     for f in ("u", "v", "p", "C"):
         close(env.get_state(f)[0], g[f][0].reshape(-1), what=f"mixing generic {f}")
     assert "us" in env.fields          # the generic kernel keeps the starred velocities as state fields
+
+
+def test_mac2d_sweep_counts_soak():
+    """More seeds for the data-dependent Jacobi trip counts: the lagged, register-resident solvers must
+    stop on exactly the sweep the reference stops on (one sweep more or less changes phi by ~1e-6)."""
+    rng = np.random.default_rng(41)
+    B, K = 12, 6
+    env = make("rayleigh", B)
+    orcs = [bo.rayleigh() for _ in range(B)]
+    env.reset()
+    [o.reset() for o in orcs]
+    for k in range(K):
+        acts = rng.uniform(-1, 1, (B, 10)) * rng.choice([0.05, 0.5, 1.0, 3.0], size=(B, 1))
+        obs, rwd, d, t = env.step(torch.as_tensor(acts), want_iters=True)
+        ref = [o.step(acts[b]) for b, o in enumerate(orcs)]
+        assert [int(x) for x in env.last_iters[0]] == [int(o.last_iters.sum()) for o in orcs], f"action {k}"
+        close(env.get_state("T"), np.stack([o.T.reshape(-1) for o in orcs]), what=f"T action {k}")
+        close(env.get_state("p"), np.stack([o.p.reshape(-1) for o in orcs]), what=f"p action {k}")
+    env = make("mixing", 4)
+    orcs = [bo.mixing() for _ in range(4)]
+    env.reset()
+    [o.reset() for o in orcs]
+    for k in range(3):
+        acts = rng.integers(0, 4, 4)
+        obs, rwd, d, t = env.step(torch.as_tensor(acts, dtype=torch.int32), want_iters=True)
+        ref = [o.step(int(acts[b])) for b, o in enumerate(orcs)]
+        assert [int(x) for x in env.last_iters[0]] == [int(o.last_iters.sum()) for o in orcs], f"mixing action {k}"
+        close(env.get_state("C"), np.stack([o.C.reshape(-1) for o in orcs]), what=f"C action {k}")
+        close(env.get_state("p"), np.stack([o.p.reshape(-1) for o in orcs]), what=f"p action {k}")
+        close(rwd, np.array([r[1] for r in ref]), rtol=1e-12, what="rwd")
