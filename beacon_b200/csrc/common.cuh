@@ -83,6 +83,19 @@ __device__ __forceinline__ double clamp01(double r)
     return hi < 0 ? 0.0 : (hi >= 0x3ff00000 ? 1.0 : r);
 }
 __device__ __forceinline__ float clamp01(float r) { return r < 0.0f ? 0.0f : (r > 1.0f ? 1.0f : r); }
+// 0.5 * clamp(r, 0, 1) (half of the minmod limiter; the halving is exact) with the clamp done on the
+// words of 0.5 r by the integer pipe: high word = max(min(hi, hi(0.5)), 0), low word cleared when
+// either bound is active (one unsigned compare covers the sign bit and hi >= hi(0.5)).
+// Same NaN / -0.0 behaviour as clamp01.
+__device__ __forceinline__ double half_clamp01(double r)
+{
+    const double hr = 0.5 * r;
+    int hi = __double2hiint(hr), lo = __double2loint(hr);
+    lo = ((unsigned)hi >= 0x3fe00000u) ? 0 : lo;
+    hi = max(min(hi, 0x3fe00000), 0);
+    return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ float half_clamp01(float r) { return 0.5f * clamp01(r); }
 __device__ __forceinline__ float fdiv(float a, float b) { return a / b; }
 
 // Branch-free square root, same idea: MUFU.RSQ64H seed, two Newton steps on 1/sqrt(x), one

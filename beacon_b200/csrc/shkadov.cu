@@ -29,7 +29,7 @@ namespace beacon {
 template <typename R> struct ShkArgs {
     // geometry / numerics
     int nx, ndt_act, n_act, n_interp, n_jets, jet_pos, jet_hw, jet_space, l_obs, n_obs, obs_stride, l_rwd;
-    int per_jet_rwd, off, jets_overlap, jets_simple, jz0, jz_len;
+    int per_jet_rwd, off, tail_aligned, jets_overlap, jets_simple, jz0, jz_len;
     R inv_dx, inv_2dx3, inv_dx3, hdt, p5d, eps, jet_amp, dx, blow_lo, blow_hi, blowup_rwd;
     double sigma;
     uint64_t seed;
@@ -82,12 +82,34 @@ __global__ void __launch_bounds__(T, MINB) shkadov_kernel(const ShkArgs<R> a)
     const bool has_jet = (a0 + C - 1 >= a.jz0) && (a0 < a.jz0 + a.jz_len) && nj > 0;
     const int tl = tid > 0 ? tid - 1 : 0, tr = tid < T - 1 ? tid + 1 : T - 1;
     const bool interior_thread = a0 >= 2 && a0 + C - 1 <= nx - 4;   // full stencil, all points updated
-    // Thread 0 (inlet) also takes the fast path: its differences are a few selects (phi = 0 on the
-    // faces up to lattice index 0, the first off+1 points are not updated), so that warp 0 does not
-    // execute both variants of the update every sub-step and stall the others at the barrier.
-    const bool first_fast = tid == 0 && C - 1 - a.off <= nx - 4;
-    const int zf = first_fast ? a.off + 2 : 0;          // faces m < zf have phi = 0
-    const int np = first_fast ? a.off + 1 : 0;          // points m < np are not updated
+    // Warp roles (warp-uniform: no warp executes two variants of the update and stalls the others at
+    // the barrier; and as few distinct loop bodies as possible, each compact: the bodies of all
+    // resident warps must stay in the instruction cache — three 40 KB bodies measured 0.7x):
+    //   FAST     every chunk of the warp is handled by ONE branch-free body.  The host aligns the
+    //            chunks so that the outlet point nx-1 is the LAST point of its chunk: the outlet copy,
+    //            the two one-sided closures of d3o2u and the not-updated point sit at compile-time
+    //            positions and are selected by `is_last`.  Thread 0 holds `off` phantom points, the
+    //            inlet point 0 and the faces with phi = 0: selects on per-thread thresholds (zero for
+    //            everybody else), confined to m < 3 when off <= 1 (F_SMALL), or for all m in warp 0
+    //            (F_LARGE) while the other warps run the body without them (F_NONE).  Lanes beyond
+    //            the domain run on constants (h = q = 1, time step 0);
+    //   IDLE     warps entirely beyond the domain only keep the barrier count;
+    //   GENERAL  anything else (tiny lattices, overlapping / dense jets): per-point index tests.
+    enum { F_NONE = 0, F_SMALL, F_LARGE, ROLE_GENERAL, ROLE_IDLE };
+    const int w_lo = (tid & ~31) * C - a.off, w_hi = w_lo + 32 * C - 1;
+    const int last_tid = (nx - 1 + a.off) / C;
+    int role = ROLE_GENERAL;
+    if (w_lo >= nx) role = ROLE_IDLE;
+    else if (a.tail_aligned && a.jets_simple && nx - 4 >= C) {
+        // (warp 0 must not hold the outlet specials too: first thread's chunk ends before nx-3)
+        if (a.off <= 1) role = F_SMALL;
+        else role = w_lo <= 0 ? F_LARGE : F_NONE;
+        if (w_lo <= 0 && last_tid == 0) role = ROLE_GENERAL;
+    }
+    const bool is_last = tid == last_tid;
+    const int zf = tid == 0 ? a.off + 2 : 0;            // faces m < zf have phi = 0
+    const int np = tid == 0 ? a.off + 1 : 0;            // points m < np are not updated
+    const R hdt_t = a0 < nx ? a.hdt : R(0);             // lanes beyond the domain stay put
     // jets: when consecutive jet zones are at least C-1 points apart a chunk meets at most one jet
     int myjet = -1;
     if (a.jets_simple && nj > 0) {
@@ -115,6 +137,7 @@ __global__ void __launch_bounds__(T, MINB) shkadov_kernel(const ShkArgs<R> a)
     }
     for (int k = tid; k < C; k += T) { s_jw[k] = R(0); s_jw[C + a.jz_len + k] = R(0); }
     for (int i = tid; i < a.ndt_act; i += T) s_alpha[i] = (R)fmin((double)i / (double)a.n_interp, 1.0);
+    for (int k = tid; k < 2 * XN * T; k += T) ex[k] = R(1);   // slots of threads beyond the domain are read (and discarded): keep them finite
 
     // ---- load state into registers ----------------------------------------------------
     R hv[C], qv[C], rh[C], rq[C];
@@ -160,11 +183,22 @@ __global__ void __launch_bounds__(T, MINB) shkadov_kernel(const ShkArgs<R> a)
         draws += (unsigned long long)a.ndt_act;
         __syncthreads();
 
-        for (int it = 0; it < a.ndt_act; it++) {
+        // One sub-step of a chunk, shkadov.py:199-236.  KIND is the warp role.
+        auto substep = [&](const int it, auto kind_tag) {
+            constexpr int KIND = decltype(kind_tag)::value;
+            constexpr bool FAST = KIND != ROLE_GENERAL;
             const int buf = it & 1;
             R *X = ex + buf * XN * T;
             // ---- boundary conditions, shkadov.py:204-207 -------------------------------
-            if (edge_thread) {
+            if (KIND == F_SMALL || KIND == F_LARGE) {
+                const R hin = R(1) + s_noise[it];
+#pragma unroll
+                for (int m = 0; m < (KIND == F_SMALL ? 2 : C); m++)
+                    if (m < np) { hv[m] = hin; qv[m] = R(1); }           // point 0 (and the phantom points left of it)
+            }
+            if (FAST) {
+                if (is_last) { hv[C - 1] = hv[C - 2]; qv[C - 1] = qv[C - 2]; }
+            } else if (edge_thread) {
 #pragma unroll
                 for (int m = 0; m < C; m++) {
                     int i = a0 + m;
@@ -182,18 +216,20 @@ __global__ void __launch_bounds__(T, MINB) shkadov_kernel(const ShkArgs<R> a)
             X[XQ0 * T + tid] = qv[0]; X[XQL2 * T + tid] = qv[C - 2]; X[XQL1 * T + tid] = qv[C - 1];
             X[XZ0 * T + tid] = zv[0]; X[XZL2 * T + tid] = zv[C - 2]; X[XZL1 * T + tid] = zv[C - 1];
             // jet amplitudes of this sub-step, shkadov.py:224-226
-            if (!a.jets_simple && (tid < nj || nj > T)) {
-                R alpha = s_alpha[it];
-                for (int j = tid; j < nj; j += T)
-                    s_jet[buf * nj + j] = a.jet_amp * ((R(1) - alpha) * s_uprev[j] + alpha * s_ucur[j]);
+            if (!FAST) {
+                if (!a.jets_simple && (tid < nj || nj > T)) {
+                    R alpha = s_alpha[it];
+                    for (int j = tid; j < nj; j += T)
+                        s_jet[buf * nj + j] = a.jet_amp * ((R(1) - alpha) * s_uprev[j] + alpha * s_ucur[j]);
+                }
             }
             __syncthreads();
 
-            // The update of a chunk.  INTERIOR chunks (every point has the full stencil and is
-            // updated: no inlet/outlet point, no phi[0]=0 face, no one-sided closure) skip all
-            // per-point index tests; the few edge threads take the general path.
-            auto update = [&](auto interior_tag) {
-                constexpr bool INTERIOR = decltype(interior_tag)::value;
+            // The update of a chunk.  UK: F_* as above; ROLE_GENERAL = per-point index tests; -1 =
+            // interior chunk of a GENERAL warp (full stencil everywhere, any jet layout).
+            auto update = [&](auto upd_tag) {
+                constexpr int UK = decltype(upd_tag)::value;
+                constexpr bool UFAST = UK == F_NONE || UK == F_SMALL || UK == F_LARGE;
                 // ---- extended stencils ---------------------------------------------------
                 R uh[C + 5];   // h at a0-2 .. a0+C+2
                 uh[0] = X[XHL2 * T + tl]; uh[1] = X[XHL1 * T + tl];
@@ -215,24 +251,23 @@ __global__ void __launch_bounds__(T, MINB) shkadov_kernel(const ShkArgs<R> a)
                     for (int k = 0; k < C + 2; k++) { dq[k] = uq[k + 1] - uq[k]; dz[k] = uz[k + 1] - uz[k]; }
 #pragma unroll
                     for (int m = 0; m < C + 1; m++) {
-                        R rqv = fdiv(dq[m], dq[m + 1] + R(1.0e-8));
-                        R rzv = fdiv(dz[m], dz[m + 1] + R(1.0e-8));
-                        // minmod max(0, min(r, 1))
-                        R pq = clamp01(rqv);
-                        R pz = clamp01(rzv);
-                        if (!INTERIOR) { if (a0 - 1 + m <= 0) { pq = R(0); pz = R(0); } }   // phi[0] = 0
-                        else if (m < 3) { if (m < zf) { pq = R(0); pz = R(0); } }
-                        Fq[m] = uq[m + 1] + (R(0.5) * pq) * dq[m + 1];
-                        Fz[m] = uz[m + 1] + (R(0.5) * pz) * dz[m + 1];
+                        // half of the minmod limiter, 0.5 max(0, min(r, 1))
+                        R pq = half_clamp01(fdiv(dq[m], dq[m + 1] + R(1.0e-8)));
+                        R pz = half_clamp01(fdiv(dz[m], dz[m + 1] + R(1.0e-8)));
+                        if (UK == ROLE_GENERAL) { if (a0 - 1 + m <= 0) { pq = R(0); pz = R(0); } }   // phi[0] = 0
+                        if (UK == F_LARGE || (UK == F_SMALL && m < 3)) { if (m < zf) { pq = R(0); pz = R(0); } }
+                        Fq[m] = uq[m + 1] + pq * dq[m + 1];
+                        Fz[m] = uz[m + 1] + pz * dz[m + 1];
                     }
                 }
                 // ---- rhs, jets, Adams-Bashforth ----------------------------------------
                 const R *sj = s_jet + buf * nj;
                 R myamp = R(0);                                  // shkadov.py:224-226, my jet only
-                if (a.jets_simple && myjet >= 0) {
+                if ((UFAST || a.jets_simple) && myjet >= 0) {
                     const R alpha = s_alpha[it];
                     myamp = a.jet_amp * ((R(1) - alpha) * s_uprev[myjet] + alpha * s_ucur[myjet]);
                 }
+                const R hdt = UFAST ? hdt_t : a.hdt;
 #pragma unroll
                 for (int m = 0; m < C; m++) {
                     const int i = a0 + m;
@@ -240,13 +275,17 @@ __global__ void __launch_bounds__(T, MINB) shkadov_kernel(const ShkArgs<R> a)
                     R dq2h = (Fz[m + 1] - Fz[m]) * a.inv_dx;
                     // d3o2u, shkadov.py:485-491 (uh[m+2] is h_i)
                     R d3 = (-uh[m + 5] + R(6) * uh[m + 4] - R(12) * uh[m + 3] + R(10) * uh[m + 2] - R(3) * uh[m + 1]) * a.inv_2dx3;
-                    if (!INTERIOR) {
+                    if (UK == ROLE_GENERAL) {
                         if (i == nx - 3) d3 = (uh[m + 4] - R(3) * uh[m + 3] + R(3) * uh[m + 2] - uh[m + 1]) * a.inv_dx3;
                         if (i == nx - 2) d3 = (-uh[m] + R(3) * uh[m + 1] - R(3) * uh[m + 2] + uh[m + 3]) * a.inv_dx3;
                     }
+                    if (UFAST) {                                  // i = nx-3 / nx-2 of the outlet chunk
+                        if (m == C - 3 && is_last) d3 = (uh[m + 4] - R(3) * uh[m + 3] + R(3) * uh[m + 2] - uh[m + 1]) * a.inv_dx3;
+                        if (m == C - 2 && is_last) d3 = (-uh[m] + R(3) * uh[m + 1] - R(3) * uh[m + 2] + uh[m + 3]) * a.inv_dx3;
+                    }
                     const R hh = hv[m];
                     R nrq = R(1.2) * dq2h - a.p5d * (hh * (d3 + R(1)) - fdiv(qv[m], hh * hh + a.eps));   // rhsq(), :507-512
-                    if (a.jets_simple) {
+                    if (UFAST || a.jets_simple) {
                         if (myjet >= 0) nrq += myamp * s_jw[kb + m];
                     } else if (has_jet) {
                         int k = i - a.jz0;
@@ -263,17 +302,42 @@ __global__ void __launch_bounds__(T, MINB) shkadov_kernel(const ShkArgs<R> a)
                             }
                         }
                     }
-                    if ((INTERIOR && (m >= 2 || m >= np)) || (!INTERIOR && i >= 1 && i <= nx - 2)) {   // adams(), :515-518
-                        hv[m] = hh + a.hdt * (R(-3) * nrh + rh[m]);
-                        qv[m] = qv[m] + a.hdt * (R(-3) * nrq + rq[m]);
+                    bool upd = true;                                              // adams(), :515-518: points 1 .. nx-2
+                    if (UK == F_SMALL && m < 2) upd = m >= np;
+                    if (UK == F_LARGE) upd = m >= np;
+                    if (UFAST && m == C - 1) upd = upd && !is_last;
+                    if (UK == ROLE_GENERAL) upd = i >= 1 && i <= nx - 2;
+                    if (upd) {
+                        hv[m] = hh + hdt * (R(-3) * nrh + rh[m]);
+                        qv[m] = qv[m] + hdt * (R(-3) * nrq + rq[m]);
                         rh[m] = nrh;
                         rq[m] = nrq;
                     }
                 }
             };
-            if (interior_thread || first_fast) update(std::true_type{});
-            else if (a0 < nx) update(std::false_type{});
-        }   // sub-steps
+            if (FAST) update(kind_tag);
+            else if (interior_thread) update(std::integral_constant<int, -1>{});
+            else if (a0 < nx) update(std::integral_constant<int, ROLE_GENERAL>{});
+        };
+
+        if (role == F_SMALL) {
+            for (int it = 0; it < a.ndt_act; it++) substep(it, std::integral_constant<int, F_SMALL>{});
+        } else if (role == F_NONE) {
+            for (int it = 0; it < a.ndt_act; it++) substep(it, std::integral_constant<int, F_NONE>{});
+        } else if (role == F_LARGE) {
+            for (int it = 0; it < a.ndt_act; it++) substep(it, std::integral_constant<int, F_LARGE>{});
+        } else if (role == ROLE_GENERAL) {
+            for (int it = 0; it < a.ndt_act; it++) substep(it, std::integral_constant<int, ROLE_GENERAL>{});
+        } else {
+            for (int it = 0; it < a.ndt_act; it++) {           // beyond the domain: jets table duty, barrier count
+                if (!a.jets_simple) {
+                    R alpha = s_alpha[it];
+                    for (int j = tid; j < nj; j += T)
+                        s_jet[(it & 1) * nj + j] = a.jet_amp * ((R(1) - alpha) * s_uprev[j] + alpha * s_ucur[j]);
+                }
+                __syncthreads();
+            }
+        }
 
         // ---- action epilogue: obs, reward, guards -----------------------------------------
         __syncthreads();
@@ -409,7 +473,11 @@ public:
         if (const char *e = getenv("BEACON_SHKADOV_CFG")) sscanf(e, "%d,%d,%d", &wc, &wt, &wm);
         bool ok = false;
 #define BEACON_SHK_TRY(CC, TT, MB)                                                             \
-        if (!ok && (wc ? (wc == CC && wt == TT && wm == MB) : true) && (long)CC * TT - 1 >= nx) { pick<CC, TT, MB>(); ok = true; }
+        if (!ok && (wc ? (wc == CC && wt == TT && wm == MB) : true) && (long)CC * TT >= nx + (CC - nx % CC) % CC) { pick<CC, TT, MB>(); ok = true; }
+#ifdef BEACON_SHK_QUICK   /* development builds: the two variants of the bench configurations only */
+        BEACON_SHK_TRY(6, 256, 2)
+        BEACON_SHK_TRY(6, 512, 1)
+#else
         BEACON_SHK_TRY(4, 128, 4)
         BEACON_SHK_TRY(4, 256, 2)
         BEACON_SHK_TRY(6, 256, 2)
@@ -426,6 +494,7 @@ public:
         BEACON_SHK_TRY(8, 384, 1)
         BEACON_SHK_TRY(12, 256, 1)
         BEACON_SHK_TRY(12, 512, 1)
+#endif
 #undef BEACON_SHK_TRY
         if (!ok) throw Error(BEACON_ERR_UNSUPPORTED, "shkadov: no kernel variant covers this nx (max 6143) or BEACON_SHKADOV_CFG is unknown");
 
@@ -441,7 +510,14 @@ public:
         a.nx = nx; a.ndt_act = p.ndt_act; a.n_act = p.n_act; a.n_interp = p.n_interp; a.n_jets = nj;
         a.jet_pos = p.jet_pos; a.jet_hw = p.jet_hw; a.jet_space = p.jet_space; a.l_obs = p.l_obs; a.n_obs = p.n_obs;
         a.obs_stride = p.obs_stride; a.l_rwd = p.l_rwd; a.per_jet_rwd = p.per_jet_rwd;
-        a.off = ((nx - 1) % C == 0) ? 1 : 0;             // keep points nx-2 and nx-1 in one chunk
+        // Chunks are shifted left by `off` phantom points so that the outlet point nx-1 is the last point
+        // of its chunk (the LAST warp role then has its special cases at compile-time positions).
+        a.off = (C - nx % C) % C;
+        a.tail_aligned = 1;
+        if ((size_t)T * C < (size_t)nx + a.off || getenv("BEACON_SHKADOV_NOALIGN")) {   // no room: old layout, general path
+            a.off = ((nx - 1) % C == 0) ? 1 : 0;         // keep points nx-2 and nx-1 in one chunk
+            a.tail_aligned = 0;
+        }
         BEACON_REQUIRE((size_t)T * C - a.off >= (size_t)nx, "shkadov: internal chunking error");
         a.jets_overlap = (nj > 1 && p.jet_space <= 2 * p.jet_hw) ? 1 : 0;
         a.jz0 = p.jet_pos - p.jet_hw;
