@@ -57,21 +57,35 @@ template <typename R> __device__ __forceinline__ bool finite_(R x) { return isfi
 // Branch-free division for the hot loops.  nvcc's IEEE fp64 division is a ~25-instruction
 // sequence with a range test and a call to a slow path per division: the branches stop the
 // scheduler from interleaving independent divisions and the kernels become latency bound.
-// fdiv: MUFU.RCP64H seed (measured max relative error 2^-19.9 on B200), ONE cubic step
-// y1 = y0 (1 + e + e^2), e = 1 - b y0 (error e^3 = 2^-60), one multiply: measured max error of the
-// quotient 2.2e-16 relative (1 ulp) over 2^28 random operands (tools/micro/rcpacc.cu); the parity
-// contract is 1e-10.  A zero / denormal / non-finite divisor or an overflowing quotient gives NaN
-// or inf like the IEEE sequence up to the case b = +-0 with a != 0 (NaN instead of +-inf); none of
-// the divisors on these paths can be exactly zero (they are sums with a positive epsilon) and
-// non-finite states are flagged in `status`.
+// fdiv: MUFU.RCP64H seed y0 (measured max relative error 2^-19.9 on B200), ONE cubic step
+// a/b = a y0 (1 + e + e^2), e = 1 - b y0 (error e^3 = 2^-60): two roundings on top of it, i.e. a
+// quotient within 2 ulp (tools/micro/rcpacc.cu measures the variants); the parity contract is
+// 1e-10.  A zero / denormal / non-finite divisor or an overflowing quotient gives NaN or inf like
+// the IEEE sequence up to the case b = +-0 with a != 0 (NaN instead of +-inf); none of the divisors
+// on these paths can be exactly zero (they are sums with a positive epsilon) and non-finite states
+// are flagged in `status`.
 __device__ __forceinline__ double fdiv(double a, double b)
 {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));
     const double e = fma(-b, y, 1.0);
-    y = fma(y, fma(e, e, e), y);
-    return a * y;
+    // a/b = (a y0)(1 + e + e^2): the product a y0 does not wait for the refinement (dependent chain
+    // MUFU -> FMA -> FMA -> FMA instead of MUFU -> FMA -> FMA -> FMA -> MUL), same four fp64 instructions
+    const double q0 = a * y;
+    return fma(q0, fma(e, e, e), q0);
 }
+// 0.5 a / b with the halving done on the exponent of the reciprocal seed by the integer pipe (the
+// seed is 1/b to 20 bits: never zero or denormal for the finite divisors of these paths).
+__device__ __forceinline__ double fdiv_half(double a, double b)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));
+    const double e = fma(-b, y, 1.0);
+    const double hy = __hiloint2double(__double2hiint(y) - 0x00100000, 0);
+    const double q0 = a * hy;
+    return fma(q0, fma(e, e, e), q0);
+}
+__device__ __forceinline__ float fdiv_half(float a, float b) { return 0.5f * (a / b); }
 // clamp(r, 0, 1) = max(0, min(r, 1)) decided on the high word with integer compares (the fp64
 // pipe is the bottleneck of these kernels): sign bit -> 0, exponent >= 0 -> 1, else r.
 // -0.0 -> 0.  A NaN ratio gives 0 or 1 instead of NaN (numpy's maximum/minimum would propagate
@@ -96,6 +110,15 @@ __device__ __forceinline__ double half_clamp01(double r)
     return __hiloint2double(hi, lo);
 }
 __device__ __forceinline__ float half_clamp01(float r) { return 0.5f * clamp01(r); }
+// clamp(hr, 0, 0.5) for an already halved ratio
+__device__ __forceinline__ double clamp0h(double hr)
+{
+    int hi = __double2hiint(hr), lo = __double2loint(hr);
+    lo = ((unsigned)hi >= 0x3fe00000u) ? 0 : lo;
+    hi = max(min(hi, 0x3fe00000), 0);
+    return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ float clamp0h(float hr) { return hr < 0.0f ? 0.0f : (hr > 0.5f ? 0.5f : hr); }
 __device__ __forceinline__ float fdiv(float a, float b) { return a / b; }
 
 // Branch-free square root, same idea: MUFU.RSQ64H seed, two Newton steps on 1/sqrt(x), one

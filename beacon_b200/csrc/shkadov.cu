@@ -31,6 +31,7 @@ template <typename R> struct ShkArgs {
     int nx, ndt_act, n_act, n_interp, n_jets, jet_pos, jet_hw, jet_space, l_obs, n_obs, obs_stride, l_rwd;
     int per_jet_rwd, off, tail_aligned, jets_overlap, jets_simple, jz0, jz_len;
     R inv_dx, inv_2dx3, inv_dx3, hdt, p5d, eps, jet_amp, dx, blow_lo, blow_hi, blowup_rwd;
+    R k3[5], kc, kc3, c12;       // d3o2u coefficients / (2 dx^3), closure 1/dx^3 and 3/dx^3, 1.2/dx (fast body)
     double sigma;
     uint64_t seed;
     int64_t env_base;
@@ -92,7 +93,8 @@ __global__ void __launch_bounds__(T, MINB) shkadov_kernel(const ShkArgs<R> a)
     //            inlet point 0 and the faces with phi = 0: selects on per-thread thresholds (zero for
     //            everybody else), confined to m < 3 when off <= 1 (F_SMALL), or for all m in warp 0
     //            (F_LARGE) while the other warps run the body without them (F_NONE).  Lanes beyond
-    //            the domain run on constants (h = q = 1, time step 0);
+    //            the domain run the same arithmetic on phantom points (never stored, never read by
+    //            a result that is kept);
     //   IDLE     warps entirely beyond the domain only keep the barrier count;
     //   GENERAL  anything else (tiny lattices, overlapping / dense jets): per-point index tests.
     enum { F_NONE = 0, F_SMALL, F_LARGE, ROLE_GENERAL, ROLE_IDLE };
@@ -109,7 +111,6 @@ __global__ void __launch_bounds__(T, MINB) shkadov_kernel(const ShkArgs<R> a)
     const bool is_last = tid == last_tid;
     const int zf = tid == 0 ? a.off + 2 : 0;            // faces m < zf have phi = 0
     const int np = tid == 0 ? a.off + 1 : 0;            // points m < np are not updated
-    const R hdt_t = a0 < nx ? a.hdt : R(0);             // lanes beyond the domain stay put
     // jets: when consecutive jet zones are at least C-1 points apart a chunk meets at most one jet
     int myjet = -1;
     if (a.jets_simple && nj > 0) {
@@ -252,8 +253,8 @@ __global__ void __launch_bounds__(T, MINB) shkadov_kernel(const ShkArgs<R> a)
 #pragma unroll
                     for (int m = 0; m < C + 1; m++) {
                         // half of the minmod limiter, 0.5 max(0, min(r, 1))
-                        R pq = half_clamp01(fdiv(dq[m], dq[m + 1] + R(1.0e-8)));
-                        R pz = half_clamp01(fdiv(dz[m], dz[m + 1] + R(1.0e-8)));
+                        R pq = clamp0h(fdiv_half(dq[m], dq[m + 1] + R(1.0e-8)));
+                        R pz = clamp0h(fdiv_half(dz[m], dz[m + 1] + R(1.0e-8)));
                         if (UK == ROLE_GENERAL) { if (a0 - 1 + m <= 0) { pq = R(0); pz = R(0); } }   // phi[0] = 0
                         if (UK == F_LARGE || (UK == F_SMALL && m < 3)) { if (m < zf) { pq = R(0); pz = R(0); } }
                         Fq[m] = uq[m + 1] + pq * dq[m + 1];
@@ -267,24 +268,35 @@ __global__ void __launch_bounds__(T, MINB) shkadov_kernel(const ShkArgs<R> a)
                     const R alpha = s_alpha[it];
                     myamp = a.jet_amp * ((R(1) - alpha) * s_uprev[myjet] + alpha * s_ucur[myjet]);
                 }
-                const R hdt = UFAST ? hdt_t : a.hdt;
+                const R hdt = a.hdt;
 #pragma unroll
                 for (int m = 0; m < C; m++) {
                     const int i = a0 + m;
                     R nrh = (Fq[m + 1] - Fq[m]) * a.inv_dx;                       // rhsh = d1tvd(q)
-                    R dq2h = (Fz[m + 1] - Fz[m]) * a.inv_dx;
-                    // d3o2u, shkadov.py:485-491 (uh[m+2] is h_i)
-                    R d3 = (-uh[m + 5] + R(6) * uh[m + 4] - R(12) * uh[m + 3] + R(10) * uh[m + 2] - R(3) * uh[m + 1]) * a.inv_2dx3;
-                    if (UK == ROLE_GENERAL) {
-                        if (i == nx - 3) d3 = (uh[m + 4] - R(3) * uh[m + 3] + R(3) * uh[m + 2] - uh[m + 1]) * a.inv_dx3;
-                        if (i == nx - 2) d3 = (-uh[m] + R(3) * uh[m + 1] - R(3) * uh[m + 2] + uh[m + 3]) * a.inv_dx3;
-                    }
-                    if (UFAST) {                                  // i = nx-3 / nx-2 of the outlet chunk
-                        if (m == C - 3 && is_last) d3 = (uh[m + 4] - R(3) * uh[m + 3] + R(3) * uh[m + 2] - uh[m + 1]) * a.inv_dx3;
-                        if (m == C - 2 && is_last) d3 = (-uh[m] + R(3) * uh[m + 1] - R(3) * uh[m + 2] + uh[m + 3]) * a.inv_dx3;
-                    }
                     const R hh = hv[m];
-                    R nrq = R(1.2) * dq2h - a.p5d * (hh * (d3 + R(1)) - fdiv(qv[m], hh * hh + a.eps));   // rhsq(), :507-512
+                    R nrq;
+                    if (UFAST) {
+                        R d3p1 = (-uh[m + 5] + R(6) * uh[m + 4] - R(12) * uh[m + 3] + R(10) * uh[m + 2] - R(3) * uh[m + 1]) * a.inv_2dx3 + R(1);
+                        if (m == C - 3) {                         // i = nx-3 / nx-2 of the outlet chunk: one-sided closures
+                            R c = fma(a.kc, uh[m + 4], R(1)); c = fma(-a.kc3, uh[m + 3], c); c = fma(a.kc3, uh[m + 2], c); c = fma(-a.kc, uh[m + 1], c);
+                            if (is_last) d3p1 = c;
+                        }
+                        if (m == C - 2) {
+                            R c = fma(-a.kc, uh[m], R(1)); c = fma(a.kc3, uh[m + 1], c); c = fma(-a.kc3, uh[m + 2], c); c = fma(a.kc, uh[m + 3], c);
+                            if (is_last) d3p1 = c;
+                        }
+                        const R t1 = fma(hh, d3p1, -fdiv(qv[m], fma(hh, hh, a.eps)));
+                        nrq = fma(a.c12, Fz[m + 1] - Fz[m], -(a.p5d * t1));                   // rhsq(), :507-512 (1.2/dx folded)
+                    } else {
+                        R dq2h = (Fz[m + 1] - Fz[m]) * a.inv_dx;
+                        // d3o2u, shkadov.py:485-491 (uh[m+2] is h_i)
+                        R d3 = (-uh[m + 5] + R(6) * uh[m + 4] - R(12) * uh[m + 3] + R(10) * uh[m + 2] - R(3) * uh[m + 1]) * a.inv_2dx3;
+                        if (UK == ROLE_GENERAL) {
+                            if (i == nx - 3) d3 = (uh[m + 4] - R(3) * uh[m + 3] + R(3) * uh[m + 2] - uh[m + 1]) * a.inv_dx3;
+                            if (i == nx - 2) d3 = (-uh[m] + R(3) * uh[m + 1] - R(3) * uh[m + 2] + uh[m + 3]) * a.inv_dx3;
+                        }
+                        nrq = R(1.2) * dq2h - a.p5d * (hh * (d3 + R(1)) - fdiv(qv[m], hh * hh + a.eps));   // rhsq(), :507-512
+                    }
                     if (UFAST || a.jets_simple) {
                         if (myjet >= 0) nrq += myamp * s_jw[kb + m];
                     } else if (has_jet) {
@@ -320,12 +332,22 @@ __global__ void __launch_bounds__(T, MINB) shkadov_kernel(const ShkArgs<R> a)
             else if (a0 < nx) update(std::integral_constant<int, ROLE_GENERAL>{});
         };
 
+        // The single-body case runs the sub-step loop unrolled by two: the register rotation of the state
+        // arrays (old values are still needed while the new ones are formed) then costs no copies
+        // (+13 % measured).  With two bodies resident (F_LARGE + F_NONE) the unrolled pair does not pay
+        // (instruction-cache footprint), they run one sub-step per trip.
+        auto run_fast = [&](auto tag, auto unroll_tag) {
+            int it = 0;
+            if (decltype(unroll_tag)::value)
+                for (; it + 1 < a.ndt_act; it += 2) { substep(it, tag); substep(it + 1, tag); }
+            for (; it < a.ndt_act; it++) substep(it, tag);
+        };
         if (role == F_SMALL) {
-            for (int it = 0; it < a.ndt_act; it++) substep(it, std::integral_constant<int, F_SMALL>{});
+            run_fast(std::integral_constant<int, F_SMALL>{}, std::true_type{});
         } else if (role == F_NONE) {
-            for (int it = 0; it < a.ndt_act; it++) substep(it, std::integral_constant<int, F_NONE>{});
+            run_fast(std::integral_constant<int, F_NONE>{}, std::false_type{});
         } else if (role == F_LARGE) {
-            for (int it = 0; it < a.ndt_act; it++) substep(it, std::integral_constant<int, F_LARGE>{});
+            run_fast(std::integral_constant<int, F_LARGE>{}, std::false_type{});
         } else if (role == ROLE_GENERAL) {
             for (int it = 0; it < a.ndt_act; it++) substep(it, std::integral_constant<int, ROLE_GENERAL>{});
         } else {
@@ -524,6 +546,11 @@ public:
         a.jets_simple = (nj > 0 && p.jet_space > 0 && (nj == 1 || p.jet_space - 2 * p.jet_hw - 1 >= C - 1) && !a.jets_overlap) ? 1 : 0;
         a.jz_len = nj > 0 ? (nj - 1) * p.jet_space + 2 * p.jet_hw + 1 : 0;
         a.inv_dx = (R)(1.0 / p.dx); a.inv_2dx3 = (R)(1.0 / (2.0 * p.dx * p.dx * p.dx)); a.inv_dx3 = (R)(1.0 / (p.dx * p.dx * p.dx));
+        {
+            const double i3 = 1.0 / (2.0 * p.dx * p.dx * p.dx), w[5] = {-3.0, 10.0, -12.0, 6.0, -1.0};
+            for (int k = 0; k < 5; k++) a.k3[k] = (R)(w[k] * i3);
+            a.kc = (R)(2.0 * i3); a.kc3 = (R)(6.0 * i3); a.c12 = (R)(1.2 / p.dx);
+        }
         a.hdt = (R)(0.5 * p.dt); a.p5d = (R)(1.0 / (5.0 * p.delta)); a.eps = (R)p.eps; a.jet_amp = (R)p.jet_amp; a.dx = (R)p.dx;
         a.blow_lo = (R)p.blow_lo; a.blow_hi = (R)p.blow_hi; a.blowup_rwd = (R)p.blowup_rwd;
         a.sigma = p.sigma; a.seed = c.seed; a.env_base = c.env_index_base;
