@@ -496,29 +496,14 @@ public:
         bool ok = false;
 #define BEACON_SHK_TRY(CC, TT, MB)                                                             \
         if (!ok && (wc ? (wc == CC && wt == TT && wm == MB) : true) && (long)CC * TT >= nx + (CC - nx % CC) % CC) { pick<CC, TT, MB>(); ok = true; }
-#ifdef BEACON_SHK_QUICK   /* development builds: the two variants of the bench configurations only */
+        // measured on B200 (profiles/sweep_shkadov_r1j_*.txt): 10 jets (nx 1350) 6,256,2; 20 jets (nx 1850)
+        // 10,192,2; 41 jets (nx 2900) 6,512,1
         BEACON_SHK_TRY(6, 256, 2)
+        BEACON_SHK_TRY(10, 192, 2)
         BEACON_SHK_TRY(6, 512, 1)
-#else
-        BEACON_SHK_TRY(4, 128, 4)
-        BEACON_SHK_TRY(4, 256, 2)
-        BEACON_SHK_TRY(6, 256, 2)
-        BEACON_SHK_TRY(8, 192, 2)
-        BEACON_SHK_TRY(5, 288, 2)
-        BEACON_SHK_TRY(7, 224, 2)
-        BEACON_SHK_TRY(9, 160, 3)
-        BEACON_SHK_TRY(9, 160, 2)
-        BEACON_SHK_TRY(4, 352, 2)
-        BEACON_SHK_TRY(4, 384, 1)
-        BEACON_SHK_TRY(11, 128, 3)
-        BEACON_SHK_TRY(8, 256, 1)
-        BEACON_SHK_TRY(6, 512, 1)
-        BEACON_SHK_TRY(8, 384, 1)
-        BEACON_SHK_TRY(12, 256, 1)
         BEACON_SHK_TRY(12, 512, 1)
-#endif
 #undef BEACON_SHK_TRY
-        if (!ok) throw Error(BEACON_ERR_UNSUPPORTED, "shkadov: no kernel variant covers this nx (max 6143) or BEACON_SHKADOV_CFG is unknown");
+        if (!ok) throw Error(BEACON_ERR_UNSUPPORTED, "shkadov: no kernel variant covers this nx (max about 6130) or BEACON_SHKADOV_CFG is unknown");
 
         size_t nb = (size_t)B * nx * sizeof(R);
         h.alloc(nb); q.alloc(nb); rhsh.alloc(nb); rhsq.alloc(nb);

@@ -17,4 +17,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 10 --csv --log-file
     python bench.py --env mixing --steps 2 --warmup 3 $B > $OUT/launches_${TAG}_mixing.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:mac_ -s 4 -c 1 -f -o $OUT/prof_${TAG}_mixing \
     python bench.py --env mixing --steps 2 --warmup 3 $B > $OUT/prof_${TAG}_mixing.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:shkadov_kernel -s 4 -c 1 -f -o $OUT/prof_${TAG}_shkadov_separable \
+    python bench.py --env shkadov_separable --steps 6 --warmup 3 $B > $OUT/prof_${TAG}_shkadov_separable.log 2>&1
 ls -la $OUT

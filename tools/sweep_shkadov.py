@@ -24,7 +24,7 @@ print(f"{B * 1e3 / ms:12.0f} env-actions/s  {ms:8.3f} ms/step")
 '''
 nj = int(sys.argv[1]) if len(sys.argv) > 1 else 10
 batches = [int(x) for x in sys.argv[2:]] or [1024, 4096]
-cfgs = ["6,256,2", "8,192,2", "5,288,2", "7,224,2", "9,160,3", "9,160,2", "4,352,2", "4,384,1", "11,128,3"] if nj <= 12 else ["6,512,1", "8,384,1", "12,256,1"]
+cfgs = os.environ["SWEEP_CFGS"].split(";") if os.environ.get("SWEEP_CFGS") else ["6,256,2", "10,192,2", "6,512,1"] if nj <= 12 else ["10,192,2", "6,512,1", "12,512,1"]
 for cfg in cfgs:
     for B in batches:
         env = dict(os.environ, BEACON_SHKADOV_CFG=cfg)
