@@ -6,12 +6,16 @@ import torch
 sys.path.insert(0, ".")
 from beacon_b200 import BatchedEnv
 
-envs = sys.argv[1:] or ["shkadov", "shkadov41", "burgers", "sloshing", "lorenz", "vortex", "rayleigh", "mixing"]
+envs = sys.argv[1:] or ["shkadov", "shkadov41", "shkadov20", "shkadov3", "burgers", "sloshing", "lorenz", "vortex", "rayleigh", "mixing"]
 rng = np.random.default_rng(0)
 for name in envs:
     kw, base = {}, name
     if name == "shkadov41":
         base, kw = "shkadov", dict(n_jets=41, per_jet_rwd=True)
+    if name == "shkadov20":
+        base, kw = "shkadov", dict(n_jets=20)
+    if name == "shkadov3":
+        base, kw = "shkadov", dict(n_jets=3)
     e = BatchedEnv(base, batch=3, **kw)
     if base == "shkadov":
         e.reset(n_warm=torch.tensor([0, 1, 2], dtype=torch.int32))
