@@ -2,6 +2,7 @@
 // per-env classes.  No torch types, plain pointers and sizes.
 #include <cstring>
 
+#include <cstdlib>
 #include "common.cuh"
 
 using namespace beacon;
@@ -56,6 +57,23 @@ template <typename F> static int create(const beacon_common *c, beacon_env **out
 }
 
 namespace beacon {
+// Device-visible alias of a page-locked host buffer (unified addressing maps every cudaHostAlloc /
+// cudaHostRegister allocation into the device address space), or NULL for pageable memory.
+static void *mapped_alias(const void *host, bool allowed)
+{
+    static const bool staged_only = getenv("BEACON_STEP_HOST_STAGED") != nullptr;   // A/B switch
+    if (!host || staged_only || !allowed) return nullptr;
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+}
+
+// One gym step with HOST buffers.  Page-locked buffers are handed to the kernel as they are: every env's
+// CTA reads its action row and writes its observation / reward / flag rows straight over PCIe when it
+// starts / finishes, so the transfers of one env overlap the compute of the others and no copy
+// is queued behind the kernel.  Pageable buffers go through device staging buffers and
+// cudaMemcpyAsync.  Either way the call returns after the stream has drained: the results are in
+// the caller's buffers.
 void Env::step_host(const void *actions, const void *noise, void *obs, void *rwd, uint8_t *done, uint8_t *trunc,
                     int32_t *status, cudaStream_t stream)
 {
@@ -68,16 +86,21 @@ void Env::step_host(const void *actions, const void *noise, void *obs, void *rwd
         d_obs.alloc(obs_bytes); d_rwd.alloc(rwd_bytes); d_done.alloc(B); d_trunc.alloc(B); d_status.alloc(B * 4);
     }
     BEACON_REQUIRE(actions && obs && rwd && done && trunc, "step_host: NULL buffer");
-    BEACON_CUDA_CHECK(cudaMemcpyAsync(d_act.ptr, actions, act_bytes, cudaMemcpyHostToDevice, stream));
-    if (noise) BEACON_CUDA_CHECK(cudaMemcpyAsync(d_noise.ptr, noise, noise_bytes, cudaMemcpyHostToDevice, stream));
-    StepArgs a{d_act.ptr, noise ? d_noise.ptr : nullptr, d_obs.ptr, d_rwd.ptr, d_done.as<uint8_t>(),
-               d_trunc.as<uint8_t>(), d_status.as<int32_t>(), nullptr, 1, stream};
+    const bool zc = host_zero_copy;
+    void *m_act = mapped_alias(actions, zc), *m_noise = mapped_alias(noise, zc), *m_obs = mapped_alias(obs, zc), *m_rwd = mapped_alias(rwd, zc);
+    void *m_done = mapped_alias(done, zc), *m_trunc = mapped_alias(trunc, zc), *m_status = mapped_alias(status, zc);
+    if (!m_act) BEACON_CUDA_CHECK(cudaMemcpyAsync(d_act.ptr, actions, act_bytes, cudaMemcpyHostToDevice, stream));
+    if (noise && !m_noise) BEACON_CUDA_CHECK(cudaMemcpyAsync(d_noise.ptr, noise, noise_bytes, cudaMemcpyHostToDevice, stream));
+    StepArgs a{m_act ? m_act : d_act.ptr, noise ? (m_noise ? m_noise : d_noise.ptr) : nullptr, m_obs ? m_obs : d_obs.ptr,
+               m_rwd ? m_rwd : d_rwd.ptr, m_done ? (uint8_t *)m_done : d_done.as<uint8_t>(),
+               m_trunc ? (uint8_t *)m_trunc : d_trunc.as<uint8_t>(),
+               (status && m_status) ? (int32_t *)m_status : d_status.as<int32_t>(), nullptr, 1, stream};
     step(a);
-    BEACON_CUDA_CHECK(cudaMemcpyAsync(obs, d_obs.ptr, obs_bytes, cudaMemcpyDeviceToHost, stream));
-    BEACON_CUDA_CHECK(cudaMemcpyAsync(rwd, d_rwd.ptr, rwd_bytes, cudaMemcpyDeviceToHost, stream));
-    BEACON_CUDA_CHECK(cudaMemcpyAsync(done, d_done.ptr, B, cudaMemcpyDeviceToHost, stream));
-    BEACON_CUDA_CHECK(cudaMemcpyAsync(trunc, d_trunc.ptr, B, cudaMemcpyDeviceToHost, stream));
-    if (status) BEACON_CUDA_CHECK(cudaMemcpyAsync(status, d_status.ptr, B * 4, cudaMemcpyDeviceToHost, stream));
+    if (!m_obs) BEACON_CUDA_CHECK(cudaMemcpyAsync(obs, d_obs.ptr, obs_bytes, cudaMemcpyDeviceToHost, stream));
+    if (!m_rwd) BEACON_CUDA_CHECK(cudaMemcpyAsync(rwd, d_rwd.ptr, rwd_bytes, cudaMemcpyDeviceToHost, stream));
+    if (!m_done) BEACON_CUDA_CHECK(cudaMemcpyAsync(done, d_done.ptr, B, cudaMemcpyDeviceToHost, stream));
+    if (!m_trunc) BEACON_CUDA_CHECK(cudaMemcpyAsync(trunc, d_trunc.ptr, B, cudaMemcpyDeviceToHost, stream));
+    if (status && !m_status) BEACON_CUDA_CHECK(cudaMemcpyAsync(status, d_status.ptr, B * 4, cudaMemcpyDeviceToHost, stream));
     BEACON_CUDA_CHECK(cudaStreamSynchronize(stream));
 }
 }  // namespace beacon

@@ -84,6 +84,7 @@ public:
         common = c;
         const int B = c.batch;
         BEACON_REQUIRE(p.ndt_act > 0, "lorenz: bad sizes");
+        host_zero_copy = false;
         info.kind = BEACON_LORENZ; info.batch = B; info.dtype = real_traits<R>::dtype; info.device = c.device;
         info.n_obs = 6; info.act_dim = 1; info.act_is_int = 1; info.rwd_dim = 1; info.n_act = p.n_act; info.noise_dim = 0;
         x.alloc((size_t)B * 3 * sizeof(R)); fx.alloc((size_t)B * 3 * sizeof(R)); stp.alloc((size_t)B * 4);
@@ -205,6 +206,7 @@ public:
         common = c;
         const int B = c.batch;
         BEACON_REQUIRE(p.ndt_act > 0, "vortex: bad sizes");
+        host_zero_copy = false;
         info.kind = BEACON_VORTEX; info.batch = B; info.dtype = real_traits<R>::dtype; info.device = c.device;
         info.n_obs = 8; info.act_dim = 2; info.act_is_int = 0; info.rwd_dim = 1; info.n_act = p.n_act; info.noise_dim = 0;
         x.alloc((size_t)B * 4 * sizeof(R)); fx.alloc((size_t)B * 4 * sizeof(R)); t.alloc((size_t)B * sizeof(R));

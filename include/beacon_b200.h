@@ -196,9 +196,12 @@ BEACON_API int beacon_env_step(beacon_env *env, const void *actions, const void 
                                uint8_t *done, uint8_t *trunc, int32_t *status, int64_t *iters,
                                int32_t n_fused, beacon_stream_t stream);
 
-/* Same as beacon_env_step with n_fused = 1 and HOST buffers: copies actions (and noise) to the
- * device, steps, copies obs/rwd/done/trunc/status back and synchronises the stream.  For
- * best throughput pass page-locked host memory. */
+/* Same as beacon_env_step with n_fused = 1 and HOST buffers; returns after the stream has drained,
+ * with obs/rwd/done/trunc/status in the caller's buffers.  Pageable buffers are staged (actions and
+ * noise copied to the device, results copied back).  Page-locked buffers (cudaHostAlloc /
+ * cudaHostRegister, e.g. torch pinned tensors) are read and written by the step kernel itself over
+ * PCIe — every env's rows move when its CTA starts / finishes, overlapped with the compute of the
+ * others (thread-per-env lorenz / vortex always stage).  BEACON_STEP_HOST_STAGED=1 forces staging. */
 BEACON_API int beacon_env_step_host(beacon_env *env, const void *actions, const void *noise, void *obs, void *rwd,
                                     uint8_t *done, uint8_t *trunc, int32_t *status, beacon_stream_t stream);
 

@@ -149,16 +149,25 @@ def test_shkadov_fused_equals_single_and_host():
     B, K = 4, 3
     acts = torch.as_tensor(rng.uniform(-1, 1, (K, B, 5)))
     noise = torch.as_tensor(rng.uniform(-5e-4, 5e-4, (K, B, 50)))
-    e1, e2, e3 = (make("shkadov", B) for _ in range(3))
-    for e in (e1, e2, e3):
+    e1, e2, e3, e4 = (make("shkadov", B) for _ in range(4))
+    for e in (e1, e2, e3, e4):
         e.reset()
     o1, r1, d1, t1 = e1.step_fused(acts, noise)
     outs = [e2.step(acts[k], noise[k]) for k in range(K)]
     assert torch.equal(o1, torch.stack([o[0] for o in outs])) and torch.equal(r1, torch.stack([o[1] for o in outs]))
     assert torch.equal(e1.get_state("h"), e2.get_state("h")) and torch.equal(e1.get_state("q"), e2.get_state("q"))
     for k in range(K):
+        # pageable inputs (staged through device buffers), page-locked outputs (written by the kernel)
         oh, rh, dh, th = e3.step_host(acts[k].numpy(), noise[k].numpy())
         assert np.array_equal(oh.numpy(), outs[k][0].cpu().numpy()) and np.array_equal(rh.numpy(), outs[k][1].cpu().numpy())
+        # everything page-locked (the kernel reads and writes the host buffers directly), and everything pageable
+        om, rm, dm, tm = e4.step_host(acts[k].pin_memory(), noise[k].pin_memory())
+        assert np.array_equal(om.numpy(), oh.numpy()) and np.array_equal(rm.numpy(), rh.numpy())
+        assert np.array_equal(dm.numpy(), dh.numpy()) and np.array_equal(tm.numpy(), th.numpy())
+    e5 = make("shkadov", B)
+    e5.reset()
+    op, rp, dp, tp = e5.step_host(acts[0].numpy(), noise[0].numpy(), out=e5.alloc_host_outputs(pinned=False))
+    assert np.array_equal(op.numpy(), outs[0][0].cpu().numpy()) and np.array_equal(rp.numpy(), outs[0][1].cpu().numpy())
 
 
 def test_shkadov_philox_noise_sharding_invariance():
