@@ -112,6 +112,36 @@ def test_shkadov_vs_oracle_resync():
         close(rwd, np.array([r[1] for r in ref]), rtol=1e-12, what="rwd")
 
 
+@pytest.mark.parametrize("kw,noalign", [
+    (dict(n_jets=4, jet_space=5.0), False),      # dense jets (spacing 25 < chunk + jet width): per-point jet table
+    (dict(n_jets=4, jet_space=3.0, L0=200.0), False),   # overlapping jets (spacing 15 < 21): generic per-jet loop
+    (dict(n_jets=10), True),                     # outlet not aligned to a chunk end: per-point index tests
+])
+def test_shkadov_general_paths_vs_oracle(kw, noalign, monkeypatch):
+    """The general (per-point index test) path of the kernel, which the standard configurations no
+    longer take: 3 actions from the oracle's state, fields within 1e-10."""
+    if noalign:
+        monkeypatch.setenv("BEACON_SHKADOV_NOALIGN", "1")
+    rng = np.random.default_rng(21)
+    B, nj = 2, kw["n_jets"]
+    env = make("shkadov", B, **kw)
+    orcs = [bo.shkadov(**kw) for _ in range(B)]
+    env.reset()
+    for o in orcs:
+        o.reset()
+    for k in range(3):
+        for f in ("h", "q", "rhsh", "rhsq", "u", "up"):
+            env.set_state(f, np.stack([getattr(o, f) for o in orcs]))
+        acts = rng.uniform(-1, 1, (B, nj))
+        noise = rng.uniform(-5e-4, 5e-4, (B, 50))
+        obs, rwd, done, trunc = env.step(torch.as_tensor(acts), noise=torch.as_tensor(noise))
+        ref = [o.step(acts[b], noise=noise[b]) for b, o in enumerate(orcs)]
+        for f in ("h", "q", "rhsh", "rhsq"):
+            close(env.get_state(f), np.stack([getattr(o, f) for o in orcs]), what=f"{f} action {k}")
+        close(obs, np.stack([r[0] for r in ref]), what="obs")
+        close(rwd, np.array([r[1] for r in ref]), rtol=1e-12, what="rwd")
+
+
 def test_shkadov_free_running_return():
     """sigma=0, 10 free-running actions: return within 1e-9."""
     rng = np.random.default_rng(12)
