@@ -12,8 +12,11 @@
 //     double-buffered shared-memory exchange: ONE __syncthreads per sub-step;
 //   * every limiter ratio / flux face is evaluated once (the face left of a chunk is the only
 //     redundant one);
+//   * ALL warps run one compact branch-free loop body: the outlet is aligned to the end of its chunk
+//     (host-chosen shift `off`), inlet / outlet special cases are per-thread selects at compile-time
+//     positions, the sub-step loop is unrolled by two (see the role table in the kernel);
 //   * inlet noise of a whole action is generated up front by Philox (or read from the caller's
-//     tensor in parity mode); jet amplitudes are interpolated by n_jets threads per sub-step;
+//     tensor in parity mode); a chunk meets at most one jet and interpolates its amplitude itself;
 //   * observation gather, per-jet reward reductions (warp shuffles) and the blow-up guard run
 //     once per action on a shared-memory copy of the final h, q.
 // HBM traffic per launch is the F-model floor (state in + out, obs/reward out); the kernel is
