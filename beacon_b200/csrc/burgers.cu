@@ -62,7 +62,8 @@ __global__ void __launch_bounds__(T) burgers_kernel(const BurArgs<R> a)
         draws += 1ull;
         const R forcing = act_val * a.amp;
 
-        for (int it = 0; it < a.ndt_act; it++) {
+        // one sub-step; run unrolled by two (the BDF2 history rotation upp <- up <- u then costs no copies)
+        auto substep = [&](const int it) {
             R(*X)[T] = ex[it & 1];
 #pragma unroll
             for (int m = 0; m < C; m++) { upp[m] = up[m]; up[m] = u[m]; }                 // :135-136
@@ -99,6 +100,11 @@ __global__ void __launch_bounds__(T) burgers_kernel(const BurArgs<R> a)
                 if (i == a.ctrl_pos) rhs += forcing;                                     // :149
                 if (i >= 1 && i <= nx - 2) u[m] = fdiv(R(4) * up[m] - upp[m] - a.two_dt * rhs, R(3));   // dert(), :247-249
             }
+        };
+        {
+            int it = 0;
+            for (; it + 1 < a.ndt_act; it += 2) { substep(it); substep(it + 1); }
+            for (; it < a.ndt_act; it++) substep(it);
         }
         // ---- obs / reward ------------------------------------------------------------------
         __syncthreads();

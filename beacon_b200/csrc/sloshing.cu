@@ -59,7 +59,9 @@ __global__ void __launch_bounds__(T) sloshing_kernel(const SloArgs<R> a)
         const size_t orow = (size_t)act * a.B + b;
         uprev = ucur;                                      // :173-174
         ucur = a.actions[orow];
-        for (int it = 0; it < a.ndt_act; it++) {
+        // one sub-step; the loop below runs it unrolled by two so that the rotation of the state
+        // registers (old values are still needed while the new ones are formed) costs no copies
+        auto substep = [&](const int it) {
             R(*X)[T] = ex[it & 1];
             // wall boundary conditions, :183-186 (ghost and its neighbour share a chunk)
 #pragma unroll
@@ -103,6 +105,11 @@ __global__ void __launch_bounds__(T) sloshing_kernel(const SloArgs<R> a)
                     rh[m] = nrh; rq[m] = nrq;
                 }
             }
+        };
+        {
+            int it = 0;
+            for (; it + 1 < a.ndt_act; it += 2) { substep(it); substep(it + 1); }
+            for (; it < a.ndt_act; it++) substep(it);
         }
         // ---- guards / obs / reward, step() :141-165 --------------------------------------------
         __syncthreads();
