@@ -6,4 +6,4 @@ driven from Python with torch CUDA tensors.  No CPU fallback.
 from ._capi import BeaconError, LIB_PATH  # noqa: F401
 from .batched import BatchedEnv  # noqa: F401
 
-__all__ = ["BatchedEnv", "BeaconError", "LIB_PATH"]
+__all__ = ["BatchedEnv", "BeaconError", "LIB_PATH"]   # also: .vector (VectorEnv, SeparableShkadov), .dist, .peer (LearnerBuffer), .envs

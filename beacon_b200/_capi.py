@@ -57,7 +57,9 @@ EXPORTS = (
     "beacon_vortex_create", "beacon_rayleigh_create", "beacon_mixing_create", "beacon_env_destroy", "beacon_env_info",
     "beacon_env_reset", "beacon_env_step", "beacon_env_step_host", "beacon_env_field", "beacon_env_get_state",
     "beacon_env_set_state", "beacon_env_launch_count", "beacon_last_error", "beacon_version",
+    "beacon_peer_alloc", "beacon_peer_export", "beacon_peer_open", "beacon_peer_close", "beacon_peer_free",
 )
+PEER_HANDLE_BYTES = 64
 
 _lib = None
 
@@ -94,6 +96,11 @@ def lib():
     L.beacon_env_set_state.argtypes = [vp, C.c_char_p, vp, vp]
     L.beacon_env_launch_count.argtypes = [vp]
     L.beacon_env_launch_count.restype = C.c_int64
+    L.beacon_peer_alloc.argtypes = [_i32, C.c_uint64, C.POINTER(vp)]
+    L.beacon_peer_export.argtypes = [vp, C.c_char_p]
+    L.beacon_peer_open.argtypes = [C.c_char_p, _i32, C.POINTER(vp)]
+    L.beacon_peer_close.argtypes = [vp]
+    L.beacon_peer_free.argtypes = [_i32, vp]
     L.beacon_last_error.restype = C.c_char_p
     L.beacon_version.restype = C.c_char_p
     _lib = L

@@ -34,6 +34,8 @@ class BatchedEnv:
     def __init__(self, name, batch, device=0, dtype=torch.float64, seed=0, env_index_base=0, init_state=None, **kwargs):
         if name not in CFG:
             raise ValueError(f"unknown env '{name}' (have {sorted(CFG)})")
+        if dtype not in (torch.float64, torch.float32):
+            raise ValueError(f"dtype must be torch.float64 or torch.float32 (the arithmetic types of the kernels), got {dtype}")
         if not torch.cuda.is_available():
             raise capi.BeaconError("beacon_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.name, self.batch, self.dtype = name, int(batch), dtype
@@ -130,29 +132,54 @@ class BatchedEnv:
             raise ValueError(f"{what}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
         return t
 
-    def reset(self, mask=None, n_warm=None, noise=None):
+    def reset(self, mask=None, n_warm=None, noise=None, max_warm=None, out=None):
         """Envs with mask[b] (all when None) go back to the reset state; shkadov runs n_warm[b]
-        zero-action warm steps first (the reference draws random.randint(0,400), shkadov.py:120)."""
+        zero-action warm steps first (the reference draws random.randint(0,400), shkadov.py:120).
+
+        Returns obs [B, n_obs].  With a mask only the rows of the masked envs are written: pass the
+        current observations as `out` to get them merged in place (VectorEnv does); without `out`
+        the rows of unmasked envs are NaN — they are NOT observations.
+        `max_warm` is an upper bound of n_warm (entries above it are clipped); giving it avoids the
+        device->host read of n_warm.max() (no host sync in the call)."""
         B = self.batch
-        obs = torch.zeros(B, self.n_obs, dtype=self.dtype, device=self.device)
-        m = None if mask is None else torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
-        w, max_warm, nz = None, 0, None
+        if out is not None:
+            obs = out
+            if obs.dtype != self.dtype or tuple(obs.shape) != (B, self.n_obs) or not obs.is_contiguous() or obs.device != self.device:
+                raise ValueError(f"reset: out must be a contiguous {self.dtype} tensor of shape {(B, self.n_obs)} on {self.device}")
+        elif mask is None:
+            obs = torch.empty(B, self.n_obs, dtype=self.dtype, device=self.device)
+        else:
+            obs = torch.full((B, self.n_obs), float("nan"), dtype=self.dtype, device=self.device)
+        m = None
+        if mask is not None:
+            m = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+            if tuple(m.shape) != (B,):
+                raise ValueError("mask must have shape [batch]")
+        w, nz = None, None
         if n_warm is not None:
             if self.name != "shkadov":
                 raise ValueError("n_warm only applies to shkadov")
-            w = torch.as_tensor(n_warm, device=self.device).to(torch.int32).contiguous()
+            w = torch.as_tensor(n_warm).to(torch.int32)
             if tuple(w.shape) != (B,):
                 raise ValueError("n_warm must have shape [batch]")
-            max_warm = int(w.max().item())
+            if max_warm is None:
+                max_warm = int(w.max().item())
+            w = w.to(self.device).contiguous()
+            max_warm = int(max_warm)
             if noise is not None:
                 nz = self._real(noise, (max_warm, B, self.noise_dim), "noise")
+        else:
+            max_warm = 0
         with torch.cuda.device(self.device):
             capi.check(self._lib.beacon_env_reset(self._h, _ptr(m), _ptr(w), _ptr(nz), max_warm, _ptr(obs), self._stream()))
         return obs
 
-    def step_fused(self, actions, noise=None, want_iters=False):
-        """K consecutive actions in one launch.  actions [K,B,act_dim] real, or [K,B] int."""
+    def step_fused(self, actions, noise=None, want_iters=False, out=None):
+        """K consecutive actions in one launch.  actions [K,B,act_dim] real, or [K,B] int.
+        `out` = (obs [K,B,n_obs], rwd [K,B,rwd_dim], done uint8 [K,B], trunc uint8 [K,B]) preallocated
+        device tensors (no allocation in the call; the flags come back as views of them)."""
         B = self.batch
+        actions = torch.as_tensor(actions)
         K = int(actions.shape[0])
         if self.act_is_int:
             a = torch.as_tensor(actions, device=self.device).to(torch.int32).contiguous()
@@ -165,10 +192,17 @@ class BatchedEnv:
             if self.noise_dim == 0:
                 raise ValueError(f"{self.name} takes no noise")
             nz = self._real(noise, (K, B, self.noise_dim), "noise")
-        obs = torch.empty(K, B, self.n_obs, dtype=self.dtype, device=self.device)
-        rwd = torch.empty(K, B, self.rwd_dim, dtype=self.dtype, device=self.device)
-        done = torch.empty(K, B, dtype=torch.uint8, device=self.device)
-        trunc = torch.empty(K, B, dtype=torch.uint8, device=self.device)
+        if out is None:
+            obs = torch.empty(K, B, self.n_obs, dtype=self.dtype, device=self.device)
+            rwd = torch.empty(K, B, self.rwd_dim, dtype=self.dtype, device=self.device)
+            done = torch.empty(K, B, dtype=torch.uint8, device=self.device)
+            trunc = torch.empty(K, B, dtype=torch.uint8, device=self.device)
+        else:
+            obs, rwd, done, trunc = out
+            for t, shp, dt, what in ((obs, (K, B, self.n_obs), self.dtype, "obs"), (rwd, (K, B, self.rwd_dim), self.dtype, "rwd"),
+                                     (done, (K, B), torch.uint8, "done"), (trunc, (K, B), torch.uint8, "trunc")):
+                if t.dtype != dt or tuple(t.shape) != shp or not t.is_contiguous() or t.device != self.device:
+                    raise ValueError(f"out.{what}: expected a contiguous {dt} tensor of shape {shp} on {self.device}")
         iters = torch.zeros(K, B, dtype=torch.int64, device=self.device) if want_iters else None
         with torch.cuda.device(self.device):
             capi.check(self._lib.beacon_env_step(self._h, _ptr(a), _ptr(nz), _ptr(obs), _ptr(rwd), _ptr(done), _ptr(trunc),
@@ -176,7 +210,31 @@ class BatchedEnv:
         self.last_iters = iters
         if self.rwd_dim == 1:
             rwd = rwd[..., 0]
+        if out is not None:
+            return obs, rwd, done.view(torch.bool), trunc.view(torch.bool)
         return obs, rwd, done.bool(), trunc.bool()
+
+    def step_into(self, actions, obs_ptr, rwd_ptr, done_ptr, trunc_ptr, noise=None):
+        """One gym step whose observation / reward / flag rows are written to RAW device addresses
+        (ints): memory this process does not own as torch tensors, e.g. this rank's slice of a
+        learner buffer mapped from another GPU (beacon_b200.peer.LearnerBuffer).  Layout as in
+        step(): obs [B,n_obs], rwd [B,rwd_dim], done / trunc uint8 [B]."""
+        B = self.batch
+        if self.act_is_int:
+            a = torch.as_tensor(actions, device=self.device).to(torch.int32).contiguous()
+            if tuple(a.shape) != (B,):
+                raise ValueError(f"actions: expected shape {(B,)}, got {tuple(a.shape)}")
+        else:
+            a = self._real(actions, (B, self.act_dim), "actions")
+        nz = None
+        if noise is not None:
+            if self.noise_dim == 0:
+                raise ValueError(f"{self.name} takes no noise")
+            nz = self._real(noise, (B, self.noise_dim), "noise")
+        with torch.cuda.device(self.device):
+            capi.check(self._lib.beacon_env_step(self._h, _ptr(a), _ptr(nz), C.c_void_p(int(obs_ptr)), C.c_void_p(int(rwd_ptr)),
+                                                 C.c_void_p(int(done_ptr)), C.c_void_p(int(trunc_ptr)), _ptr(self.status), None, 1,
+                                                 self._stream()))
 
     def step(self, actions, noise=None, want_iters=False):
         """One gym step for the whole batch. actions [B,act_dim] real or [B] int."""
@@ -190,22 +248,39 @@ class BatchedEnv:
         actions, the step kernel, D2H copy of obs/rewards/flags, stream sync — all inside the call
         (beacon_env_step_host).  `out` may hold preallocated pinned tensors (obs, rwd, done, trunc)."""
         B = self.batch
-        if self.act_is_int:
-            a = torch.as_tensor(actions).to(torch.int32).contiguous()
-        else:
-            a = torch.as_tensor(actions).to(self.dtype).contiguous()
-        if a.is_cuda:
-            raise ValueError("step_host takes host buffers")
+
+        def host(t, dt, shape, what):
+            t = torch.as_tensor(t)
+            if t.is_cuda:
+                raise ValueError(f"step_host: {what} must be a host buffer")
+            if t.dtype != dt:
+                t = t.to(dt)
+            t = t.contiguous()
+            if tuple(t.shape) != tuple(shape):
+                raise ValueError(f"step_host: {what}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
+            return t
+
+        a = host(actions, torch.int32, (B,), "actions") if self.act_is_int else host(actions, self.dtype, (B, self.act_dim), "actions")
         nz = None
         if noise is not None:
-            nz = torch.as_tensor(noise).to(self.dtype).contiguous()
+            if self.noise_dim == 0:
+                raise ValueError(f"{self.name} takes no noise")
+            nz = host(noise, self.dtype, (B, self.noise_dim), "noise")
         if out is None:
             out = self.alloc_host_outputs()
+        if len(out) != 5:
+            raise ValueError("step_host: out must be (obs, rwd, done, trunc, status) as returned by alloc_host_outputs()")
         obs, rwd, done, trunc, status = out
+        # the native side writes B*n_obs*sizeof(real) ... bytes into these buffers: refuse anything else
+        for t, dt, shp, what in ((obs, self.dtype, (B, self.n_obs), "obs"), (rwd, self.dtype, (B, self.rwd_dim), "rwd"),
+                                 (done, torch.uint8, (B,), "done"), (trunc, torch.uint8, (B,), "trunc"),
+                                 (status, torch.int32, (B,), "status")):
+            if not isinstance(t, torch.Tensor) or t.is_cuda or t.dtype != dt or tuple(t.shape) != shp or not t.is_contiguous():
+                raise ValueError(f"step_host: out.{what} must be a contiguous host {dt} tensor of shape {shp}")
         with torch.cuda.device(self.device):
             capi.check(self._lib.beacon_env_step_host(self._h, _ptr(a), _ptr(nz), _ptr(obs), _ptr(rwd), _ptr(done),
                                                       _ptr(trunc), _ptr(status), self._stream()))
-        return obs, (rwd[:, 0] if self.rwd_dim == 1 else rwd), done, trunc
+        return obs, (rwd[:, 0] if self.rwd_dim == 1 else rwd), done.bool(), trunc.bool()
 
     def alloc_host_outputs(self, pinned=True):
         B = self.batch
@@ -229,7 +304,9 @@ class BatchedEnv:
             torch.cuda.current_stream(self.device).synchronize()   # `t` may be a temporary
 
     def state_dict(self):
-        """Full device state (binary checkpoint; SURVEY.md §5 'Checkpoint / resume')."""
+        """Full device state (binary checkpoint; SURVEY.md §5 'Checkpoint / resume'), including the
+        per-env Philox draw counter of the inlet noise ("draws", shkadov / burgers): a restored env
+        continues the same noise stream as an uninterrupted one."""
         return {k: self.get_state(k).cpu() for k in self.fields}
 
     def load_state_dict(self, sd):

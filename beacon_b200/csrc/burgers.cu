@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(T) burgers_kernel(const BurArgs<R> a)
     unsigned long long draws = a.draws[b];
     R act_val = resetting ? R(0) : a.a_cur[b];
     const int n_actions = resetting ? 0 : a.n_fused;
+    int status = 0;                                     // OR of the beacon_status bits of all fused actions
 
     for (int act = 0; act < n_actions; act++) {
         const size_t orow = (size_t)act * a.B + b;
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(T) burgers_kernel(const BurArgs<R> a)
             a.rwd[orow] = -tot * a.dx;
             bool horizon = stp == a.n_act - 1;
             a.done[orow] = horizon; a.trunc[orow] = horizon;
-            if (a.status) a.status[b] = bad ? BEACON_STATUS_NONFINITE : 0;
+            if (bad) status |= BEACON_STATUS_NONFINITE;
         }
         stp += 1;
         __syncthreads();
@@ -140,7 +141,10 @@ __global__ void __launch_bounds__(T) burgers_kernel(const BurArgs<R> a)
         int i = a0 + m;
         if (i >= 0 && i < nx) { a.u[row + i] = u[m]; a.up[row + i] = up[m]; a.upp[row + i] = upp[m]; }
     }
-    if (tid == 0) { a.stp[b] = stp; a.draws[b] = draws; a.a_cur[b] = act_val; }
+    if (tid == 0) {
+        a.stp[b] = stp; a.draws[b] = draws; a.a_cur[b] = act_val;
+        if (!resetting && a.status) a.status[b] = status;
+    }
 }
 
 template <typename R> class BurgersEnv : public Env {
@@ -169,6 +173,7 @@ public:
         u.alloc(nb); up.alloc(nb); upp.alloc(nb); a_cur.alloc(B * sizeof(R)); stp.alloc(B * 4); draws.alloc(B * 8);
         add_field("u", u.ptr, nx); add_field("up", up.ptr, nx); add_field("upp", upp.ptr, nx);
         add_field("a", a_cur.ptr, 1); add_field("stp", stp.ptr, 1, true);
+        add_field("draws", draws.ptr, 2, true);       // uint64 Philox draw counter as two int32 words (checkpoint / resume)
         BurArgs<R> &a = base;
         a.nx = nx; a.ndt_act = p.ndt_act; a.n_act = p.n_act; a.ctrl_pos = p.ctrl_pos; a.n_obs = p.n_obs_pts;
         a.off = ((nx - 1) % C == 0) ? 1 : 0; a.B = B;

@@ -228,9 +228,54 @@ int beacon_env_set_state(beacon_env *env, const char *field, const void *buf, be
     return copy_state(env, field, nullptr, buf, stream);
 }
 
+int beacon_peer_alloc(int32_t device, uint64_t bytes, void **ptr)
+{
+    return guard([&] {
+        BEACON_REQUIRE(ptr && bytes > 0, "peer_alloc: bad argument");
+        BEACON_CUDA_CHECK(cudaSetDevice(device));
+        BEACON_CUDA_CHECK(cudaMalloc(ptr, (size_t)bytes));
+        BEACON_CUDA_CHECK(cudaMemset(*ptr, 0, (size_t)bytes));
+    });
+}
+int beacon_peer_export(void *ptr, uint8_t handle[BEACON_PEER_HANDLE_BYTES])
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == BEACON_PEER_HANDLE_BYTES, "IPC handle size");
+    return guard([&] {
+        BEACON_REQUIRE(ptr && handle, "peer_export: NULL argument");
+        cudaIpcMemHandle_t h;
+        BEACON_CUDA_CHECK(cudaIpcGetMemHandle(&h, ptr));
+        memcpy(handle, &h, sizeof(h));
+    });
+}
+int beacon_peer_open(const uint8_t handle[BEACON_PEER_HANDLE_BYTES], int32_t device, void **ptr)
+{
+    return guard([&] {
+        BEACON_REQUIRE(ptr && handle, "peer_open: NULL argument");
+        BEACON_CUDA_CHECK(cudaSetDevice(device));
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handle, sizeof(h));
+        BEACON_CUDA_CHECK(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    });
+}
+int beacon_peer_close(void *ptr)
+{
+    return guard([&] {
+        BEACON_REQUIRE(ptr, "peer_close: NULL argument");
+        BEACON_CUDA_CHECK(cudaIpcCloseMemHandle(ptr));
+    });
+}
+int beacon_peer_free(int32_t device, void *ptr)
+{
+    return guard([&] {
+        BEACON_REQUIRE(ptr, "peer_free: NULL argument");
+        BEACON_CUDA_CHECK(cudaSetDevice(device));
+        BEACON_CUDA_CHECK(cudaFree(ptr));
+    });
+}
+
 int64_t beacon_env_launch_count(const beacon_env *env) { return env ? env->impl->launches : 0; }
 
 const char *beacon_last_error(void) { return g_last_error.c_str(); }
-const char *beacon_version(void) { return "beacon_b200 0.1 (sm_100a)"; }
+const char *beacon_version(void) { return "beacon_b200 0.2 (sm_100a)"; }
 
 }  // extern "C"

@@ -50,6 +50,7 @@ template <typename R> struct ShkArgs {
     const R *noise;              // nullable [K,B,ndt_act]
     const uint8_t *mask;         // reset only, nullable
     const int32_t *n_warm;       // reset only, nullable
+    const int32_t *order;        // reset only, nullable: CTA -> env permutation (longest warm-up first)
     R *obs, *rwd;
     uint8_t *done, *trunc;
     int32_t *status;
@@ -63,7 +64,7 @@ __global__ void __launch_bounds__(T, MINB) shkadov_kernel(const ShkArgs<R> a)
 {
     static_assert(C >= 3, "halo exchange needs at least 3 points per thread");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tid = threadIdx.x, b = blockIdx.x;
+    const int tid = threadIdx.x, b = a.order ? a.order[blockIdx.x] : (int)blockIdx.x;
     const int nx = a.nx, nj = a.n_jets;
 
     if (a.mode == 1 && a.mask && !a.mask[b]) return;
@@ -455,12 +456,39 @@ __global__ void __launch_bounds__(T, MINB) shkadov_kernel(const ShkArgs<R> a)
     }
 }
 
+// Reset order: CTAs are handed to the SMs in blockIdx order, and a reset with random warm steps
+// (shkadov.py:118-123, U{0..400} actions per env) finishes when its longest env does.  One small CTA
+// sorts the env indices by decreasing n_warm (counting sort over <= 2048 bins; ties in any order —
+// only the schedule depends on it, never a result) so that the longest envs start first and the
+// short ones fill the tail.
+__global__ void __launch_bounds__(1024) shkadov_order_kernel(const int32_t *n_warm, const uint8_t *mask, int B, int max_warm, int32_t *order)
+{
+    constexpr int NB = 2048;
+    __shared__ int hist[NB + 1];
+    const int tid = threadIdx.x, T = blockDim.x;
+    for (int k = tid; k <= NB; k += T) hist[k] = 0;
+    __syncthreads();
+    auto bin_of = [&](int b) {
+        int w = (mask && !mask[b]) ? 0 : min(max(n_warm[b], 0), max_warm);
+        int q = (int)(((long long)w * (NB - 1)) / (long long)(max_warm > 0 ? max_warm : 1));
+        return NB - 1 - q;                                  // bin 0 = longest
+    };
+    for (int b = tid; b < B; b += T) atomicAdd(&hist[bin_of(b)], 1);
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int k = 0; k < NB; k++) { int c = hist[k]; hist[k] = run; run += c; }
+    }
+    __syncthreads();
+    for (int b = tid; b < B; b += T) order[atomicAdd(&hist[bin_of(b)], 1)] = b;
+}
+
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
 template <typename R> class ShkadovEnv : public Env {
     beacon_shkadov_params p;
-    DeviceBuffer h, q, rhsh, rhsq, u_cur, u_prev, stp, draws, h_init, q_init;
+    DeviceBuffer h, q, rhsh, rhsq, u_cur, u_prev, stp, draws, h_init, q_init, order;
     ShkArgs<R> base{};
     int C = 0, T = 0;
     size_t smem = 0;
@@ -515,6 +543,7 @@ public:
         upload_as<R>(h_init, h0, nx); upload_as<R>(q_init, q0, nx);
         add_field("h", h.ptr, nx); add_field("q", q.ptr, nx); add_field("rhsh", rhsh.ptr, nx); add_field("rhsq", rhsq.ptr, nx);
         add_field("u", u_cur.ptr, nj); add_field("up", u_prev.ptr, nj); add_field("stp", stp.ptr, 1, true);
+        add_field("draws", draws.ptr, 2, true);        // uint64 Philox draw counter as two int32 words (checkpoint / resume)
 
         ShkArgs<R> &a = base;
         a.nx = nx; a.ndt_act = p.ndt_act; a.n_act = p.n_act; a.n_interp = p.n_interp; a.n_jets = nj;
@@ -566,6 +595,14 @@ public:
         a.mode = 1; a.mask = r.mask; a.n_warm = r.n_warm; a.max_warm = r.n_warm ? r.max_warm : 0;
         a.noise = (const R *)r.noise; a.obs = (R *)r.obs; a.status = nullptr; a.n_fused = 0;
         BEACON_REQUIRE(r.obs != nullptr, "reset: obs must not be NULL");
+        static const bool in_order = getenv("BEACON_SHKADOV_RESET_INORDER") != nullptr;   // A/B switch
+        if (r.n_warm && a.max_warm > 0 && a.B > 1 && !in_order) {
+            if (!order.ptr) order.alloc((size_t)a.B * sizeof(int32_t));
+            shkadov_order_kernel<<<1, 1024, 0, r.stream>>>(r.n_warm, r.mask, a.B, a.max_warm, order.as<int32_t>());
+            BEACON_CUDA_CHECK(cudaGetLastError());
+            launches++;
+            a.order = order.as<int32_t>();
+        }
         launch(a, r.stream);
     }
 

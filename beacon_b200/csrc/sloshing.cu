@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(T) sloshing_kernel(const SloArgs<R> a)
     int stp = resetting ? 0 : a.stp[b];
     R ucur = resetting ? R(0) : a.u_cur[b], uprev = resetting ? R(0) : a.u_prev[b];
     const int n_actions = resetting ? 0 : a.n_fused;
+    int status = 0;                                     // OR of the beacon_status bits of all fused actions
 
     for (int act = 0; act < n_actions; act++) {
         const size_t orow = (size_t)act * a.B + b;
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(T) sloshing_kernel(const SloArgs<R> a)
             a.rwd[orow] = R(0) - rsqrt_(tot) * a.dx - a.alpha_pen * rabs(a.amp * ucur);                // :235-244
             bool horizon = stp == a.n_act - 1, blow = fl & 1;
             a.done[orow] = horizon || blow; a.trunc[orow] = horizon && !blow;
-            if (a.status) a.status[b] = (blow ? BEACON_STATUS_BLOWUP : 0) | ((fl & 4) ? BEACON_STATUS_NONFINITE : 0);
+            status |= (blow ? BEACON_STATUS_BLOWUP : 0) | ((fl & 4) ? BEACON_STATUS_NONFINITE : 0);
         }
         stp += 1;
         __syncthreads();
@@ -149,7 +150,10 @@ __global__ void __launch_bounds__(T) sloshing_kernel(const SloArgs<R> a)
         int i = a0 + m;
         if (i >= 0 && i < n2) { a.h[row + i] = h[m]; a.q[row + i] = q[m]; a.rhsh[row + i] = rh[m]; a.rhsq[row + i] = rq[m]; }
     }
-    if (tid == 0) { a.stp[b] = stp; a.u_cur[b] = ucur; a.u_prev[b] = uprev; }
+    if (tid == 0) {
+        a.stp[b] = stp; a.u_cur[b] = ucur; a.u_prev[b] = uprev;
+        if (!resetting && a.status) a.status[b] = status;
+    }
 }
 
 template <typename R> class SloshingEnv : public Env {

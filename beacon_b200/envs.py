@@ -49,7 +49,7 @@ class _Single:
     def __getattr__(self, name):
         if name.startswith("_"):
             raise AttributeError(name)
-        if name in self._fields:
+        if name in self._fields and name in self._env.fields:
             v = self._env.get_state(name)[0].cpu().numpy()
             shape = self._shape(name)
             return v.reshape(shape) if shape else v
@@ -107,11 +107,13 @@ class _Single:
         n = d["n_warmup"] if n is None else int(n)
         e = self._env
         a = e.get_state("u" if self._name in ("shkadov", "sloshing") else "a")
+        stp = e.get_state("stp")          # the reference's warmup() calls solve() only: the step counter does not move
         left = n
         while left > 0:
             k = min(50, left)
             e.step_fused(a.reshape(1, 1, -1).expand(k, 1, -1).contiguous())
             left -= k
+        e.set_state("stp", stp)
 
     def close(self):
         self._env.close()

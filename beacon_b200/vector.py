@@ -34,27 +34,30 @@ class VectorEnv:
         return torch.randint(0, self.rand_steps + 1, (self.num_envs,), generator=self._gen, device=self.env.device,
                              dtype=torch.int32)
 
-    def reset(self, mask=None):
-        obs = self.env.reset(mask=mask, n_warm=self._n_warm())
+    def reset(self, mask=None, out=None):
+        obs = self.env.reset(mask=mask, n_warm=self._n_warm(), max_warm=self.rand_steps if self.rand_init else None, out=out)
         if mask is None:
             self.episode_return.zero_(); self.episode_length.zero_()
         else:
             m = torch.as_tensor(mask, device=self.env.device).bool()
-            self.episode_return[m] = 0; self.episode_length[m] = 0
+            self.episode_return.masked_fill_(m, 0); self.episode_length.masked_fill_(m, 0)
         return obs
 
     def step(self, actions, noise=None):
+        """No device->host synchronisation: the masked reset is launched unconditionally after every step
+        (its CTAs return at once for envs that are not done) and writes the first observation of the new
+        episode over the rows of the finished envs; `info` holds device tensors — `final_obs`,
+        `episode_return`, `episode_length` are meaningful where `done` is set."""
         obs, rwd, done, trunc = self.env.step(actions, noise=noise)
         r = rwd if rwd.dim() == 1 else rwd.sum(-1)
         self.episode_return += r
         self.episode_length += 1
         info = {}
-        if self.auto_reset and bool(done.any()):
+        if self.auto_reset:
             info["final_obs"] = obs.clone()
             info["episode_return"] = self.episode_return.clone()
             info["episode_length"] = self.episode_length.clone()
-            new_obs = self.reset(mask=done)
-            obs = torch.where(done[:, None], new_obs, obs)
+            obs = self.reset(mask=done, out=obs)
         return obs, rwd, done, trunc, info
 
     def close(self):
@@ -76,8 +79,11 @@ class SeparableShkadov:
         self.num_envs, self.n_jets = num_envs, n_jets
         self.n_obs = self.env.n_obs // n_jets
 
-    def reset(self, mask=None, n_warm=None):
-        return self.env.reset(mask=mask, n_warm=n_warm).view(self.num_envs, self.n_jets, self.n_obs)
+    def reset(self, mask=None, n_warm=None, out=None):
+        """With a mask only the masked envs' rows are written (pass the current observations as `out`,
+        [B, n_jets, n_obs] contiguous, to have them merged in place; otherwise the other rows are NaN)."""
+        o = None if out is None else out.view(self.num_envs, self.n_jets * self.n_obs)
+        return self.env.reset(mask=mask, n_warm=n_warm, out=o).view(self.num_envs, self.n_jets, self.n_obs)
 
     def step(self, actions, noise=None):
         obs, rwd, done, trunc = self.env.step(actions, noise=noise)

@@ -209,12 +209,35 @@ BEACON_API int beacon_env_step_host(beacon_env *env, const void *actions, const 
 /* Field names follow the reference attributes: shkadov "h","q","rhsh","rhsq","u","up","stp";
  * burgers "u","up","upp","a","stp"; sloshing "h","q","rhsh","rhsq","u","up","stp";
  * lorenz/vortex "x","fx","stp" (+ vortex "t","y"); rayleigh "u","v","p","T","a","obs","stp";
- * mixing "u","v","p","C","obs","stp".  Real fields are `dtype`, "stp" is int32.
+ * mixing "u","v","p","C","obs","stp".  Real fields are `dtype`, "stp" is int32; shkadov and burgers
+ * also expose "draws": the uint64 Philox draw counter of the inlet noise as two int32 words, so that a
+ * state dump restores the noise stream too.
  * beacon_env_field reports the per-env element count and whether the field is integer. */
 BEACON_API int beacon_env_field(const beacon_env *env, int32_t index, const char **name, int64_t *count,
                                 int32_t *is_int);
 BEACON_API int beacon_env_get_state(beacon_env *env, const char *field, void *buf, beacon_stream_t stream);
 BEACON_API int beacon_env_set_state(beacon_env *env, const char *field, const void *buf, beacon_stream_t stream);
+
+/* ---- learner-rank buffers in peer memory (multi-GPU, one process per GPU) -------------
+ * The only exchange of the path is the gather of observations / rewards / flags to the learner
+ * rank (reference call sites whose outputs travel: get_obs / get_rwd,
+ * shkadov.py:239-264, rayleigh.py:243-275).  Instead of a collective after the step, the learner
+ * exports ONE device allocation over CUDA IPC, every other process maps it, and beacon_env_step is
+ * given obs / rwd / done / trunc pointers INSIDE that mapping: each env's CTA then writes its rows
+ * straight into the learner GPU's HBM over NVLink when it finishes (the same mechanism as the
+ * zero-copy host path of beacon_env_step_host), overlapped with the compute of the other envs.
+ * Completion is the caller's business (a stream-ordered barrier after the step).
+ *   beacon_peer_alloc   cudaMalloc'ed, zero-filled buffer on `device` (IPC needs an allocation base)
+ *   beacon_peer_export  64-byte cudaIpcMemHandle_t of a beacon_peer_alloc'ed buffer
+ *   beacon_peer_open    map an exported buffer into this process for use from `device`
+ *   beacon_peer_close   unmap (importing processes);  beacon_peer_free: release (exporting process)
+ */
+#define BEACON_PEER_HANDLE_BYTES 64
+BEACON_API int beacon_peer_alloc(int32_t device, uint64_t bytes, void **ptr);
+BEACON_API int beacon_peer_export(void *ptr, uint8_t handle[BEACON_PEER_HANDLE_BYTES]);
+BEACON_API int beacon_peer_open(const uint8_t handle[BEACON_PEER_HANDLE_BYTES], int32_t device, void **ptr);
+BEACON_API int beacon_peer_close(void *ptr);
+BEACON_API int beacon_peer_free(int32_t device, void *ptr);
 
 /* number of kernel launches issued by this handle so far (bench.py's gpu_launches claim) */
 BEACON_API int64_t beacon_env_launch_count(const beacon_env *env);

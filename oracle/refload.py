@@ -15,8 +15,11 @@ import os
 import sys
 import warnings
 
-REF_ROOT = os.environ.get("BEACON_REFERENCE", "/root/reference")
-_SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "refshim")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+# the checkout in the build container, else the copy staged by oracle/make_ref.py (travels to the GPU box for
+# the CPU-baseline arm of bench.py only; tests never read it)
+REF_ROOT = os.environ.get("BEACON_REFERENCE") or ("/root/reference" if os.path.isdir("/root/reference/beacon") else os.path.join(_HERE, "_ref"))
+_SHIM = os.path.join(_HERE, "refshim")
 
 _MODULE_OF = {"shkadov_separable": "shkadov"}
 

@@ -97,29 +97,45 @@ def test_separable_many_actuators_per_jet_rewards_add_up():
     assert relerr(sep.get_state("h")[5], o.h) <= 1e-10
 
 
-def test_rayleigh_4096_envs_one_action(golden):
-    """configs[4]: rayleigh-v0, 4096 envs.  Equal actions -> bitwise equal rows and sweep counts,
-    equal to the reference's golden step; rows with their own action do not disturb them."""
+def test_rayleigh_4096_envs_two_actions(golden):
+    """configs[4]: rayleigh-v0, 4096 envs.  Action 1 = the reference's first golden action on every env
+    (zeros: one sweep per solve); action 2 = the SECOND golden action (11 993 Jacobi sweeps in the
+    reference) on the even rows and independent random actions on the odd rows, five of which are
+    followed by the oracle.  Equal actions -> bitwise equal rows and sweep counts, equal to the golden
+    fields; the multi-sweep path at full batch is anchored on golden and oracle rows."""
     g = golden("rayleigh")
     B = 4096
     rng = np.random.default_rng(24)
-    acts = np.broadcast_to(g["actions"][0], (B, 10)).copy()
-    odd = np.arange(1, B, 2)
-    acts[odd] = rng.uniform(-1, 1, (odd.size, 10))
     env = make("rayleigh", B)
     env.reset()
+    a0 = np.broadcast_to(g["actions"][0], (B, 10)).copy()
+    obs, rwd, done, trunc = env.step(torch.as_tensor(a0), want_iters=True)
+    assert bool((env.last_iters[0] == int(g["itp"][0].sum())).all())
+    acts = np.broadcast_to(g["actions"][1], (B, 10)).copy()
+    odd = np.arange(1, B, 2)
+    acts[odd] = rng.uniform(-1, 1, (odd.size, 10))
     obs, rwd, done, trunc = env.step(torch.as_tensor(acts), want_iters=True)
     it = env.last_iters[0]
     T = env.get_state("T")
     assert int(env.status.max()) == 0
-    assert int(it[0]) == int(g["itp"][0].sum())
+    assert int(g["itp"][1].sum()) > 10000 and int(it[0]) == int(g["itp"][1].sum()), "golden action 1 sweep count"
     even = torch.arange(0, B, 2, device=T.device)
     assert bool((it[even] == it[0]).all())
     assert torch.equal(T[even], T[0:1].expand(even.numel(), -1)) and torch.equal(obs[even], obs[0:1].expand(even.numel(), -1))
-    for f, name in (("u", "u"), ("v", "v"), ("p", "p"), ("T", "T")):
-        assert relerr(env.get_state(f)[4094], g[name][0].reshape(-1)) <= 1e-10, f
-    assert abs(float(rwd[0]) - float(g["rwd"][0])) <= 1e-12 * abs(float(g["rwd"][0]))
+    for f in ("u", "v", "p", "T"):
+        assert relerr(env.get_state(f)[4094], g[f][1].reshape(-1)) <= 1e-10, f
+    assert relerr(obs[2], g["obs"][1]) <= 1e-10
+    assert abs(float(rwd[0]) - float(g["rwd"][1])) <= 1e-12 * abs(float(g["rwd"][1]))
     assert len(torch.unique(it[odd])) > 10            # data-dependent trip counts really differ across the batch
+    for b in (1, 777, 2049, 3333, 4095):              # oracle rows with their own random action
+        o = bo.rayleigh()
+        o.reset()
+        o.step(g["actions"][0].copy())
+        ro = o.step(acts[b].copy())
+        assert int(it[b]) == int(o.last_iters.sum()), f"row {b}: sweep count differs from the oracle"
+        for f in ("u", "v", "p", "T"):
+            assert relerr(env.get_state(f)[b], getattr(o, f).reshape(-1)) <= 1e-10, (b, f)
+        assert relerr(obs[b], ro[0]) <= 1e-10 and abs(float(rwd[b]) - ro[1]) <= 1e-12 * abs(ro[1])
 
 
 def test_mixing_1024_envs_one_action(golden):
