@@ -38,15 +38,19 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    os.makedirs(os.path.join(LIBDIR, "obj"), exist_ok=True)
+def build(force=False, verbose=False, tag=None, defines=()):
+    """tag / defines: A/B variants for tuning (tools/ab.sh): objects in lib/obj_<tag>/, library lib/libbeacon_b200_<tag>.so,
+    extra -D flags; the product build has neither."""
+    objdir = os.path.join(LIBDIR, "obj" + (f"_{tag}" if tag else ""))
+    LIB = os.path.join(LIBDIR, "libbeacon_b200" + (f"_{tag}" if tag else "") + ".so")
+    os.makedirs(objdir, exist_ok=True)
     objs, jobs = [], []
     for src in SOURCES:
         s = os.path.join(CSRC, src)
-        o = os.path.join(LIBDIR, "obj", src.replace(".cu", ".o"))
+        o = os.path.join(objdir, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + HEADERS):
-            jobs.append([nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
+            jobs.append([nvcc()] + NVCC_FLAGS + list(defines) + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
     if jobs:
         with cf.ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:
             for cmd, res in zip(jobs, ex.map(lambda c: subprocess.run(c, capture_output=True, text=True), jobs)):
@@ -60,7 +64,7 @@ def build(force=False, verbose=False):
         if res.returncode != 0:
             raise RuntimeError("link failed: %s\n%s" % (" ".join(cmd), res.stderr))
     census = os.path.join(LIBDIR, "sass_census.json")
-    if jobs or force or _stale(census, objs):
+    if not tag and (jobs or force or _stale(census, objs)):
         # static SASS census of the hot loops (fp64 / shared-memory instructions per sub-step and per Jacobi sweep):
         # bench.py turns it into the in-run roofline fraction
         tool = os.path.join(HERE, "..", "tools", "sass_census.py")
@@ -71,4 +75,5 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    tag = next((a.split("=", 1)[1] for a in sys.argv if a.startswith("--tag=")), None)
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, tag=tag, defines=[a for a in sys.argv if a.startswith("-D")]))

@@ -514,6 +514,31 @@ __device__ __noinline__ void transport_wavefront_f64(uint32_t sAA, uint32_t sWW,
 }
 
 // ---------------------------------------------------------------------------------------
+// `!(err > tol)` of one Jacobi sweep decided in fp64: the per-thread residuals `mine` are summed by the
+// xor butterfly (16, 8, 4, 2, 1) and the warp partials by a pairwise tree, the same order in every thread.
+// Called by ALL threads of the CTA (uniform branch), only when the fp32 total of the fast path lies within
+// 1e-4 tol of tol; out of line so that the sweep loop stays compact.
+// ---------------------------------------------------------------------------------------
+template <typename R, int NW>
+__device__ __noinline__ bool residual_converged_exact(R mine, R *s_exact, R tol)
+{
+    R v = mine;
+#pragma unroll
+    for (int st = 0; st < 5; st++) v += __shfl_xor_sync(0xffffffffu, v, 16 >> st);
+    if ((threadIdx.x & 31) == 0) s_exact[threadIdx.x >> 5] = v;
+    __syncthreads();
+    R q[NW];
+#pragma unroll
+    for (int w = 0; w < NW; w++) q[w] = s_exact[w];
+#pragma unroll
+    for (int st = 1; st < NW; st *= 2)
+#pragma unroll
+        for (int w = 0; w + st < NW; w += 2 * st) q[w] += q[w + st];
+    __syncthreads();
+    return !(q[0] > tol);
+}
+
+// ---------------------------------------------------------------------------------------
 // Register-resident variant (rayleigh 50x50: five planes fit twice per SM).
 //   * shared memory: two phi exchange planes (row stride LDP = 57 doubles: with 2x5 tiles laid
 //     out 10 per tile-row the 64-bit bank index of a lane's tile origin is 5*lane mod 16 ->
@@ -542,7 +567,8 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
     static_assert(NX % TI == 0 && NY % TJ == 0 && TILES <= T, "tiles must cover the grid exactly");
     static_assert(NX <= 64, "transport wavefront: two rows per lane");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ R s_part[2][NW];
+    __shared__ __align__(16) float s_part[2][NW];     // fp32 warp partials of the residual (see the Poisson section)
+    __shared__ R s_exact[NW];                         // fp64 warp partials, only when the fp32 total is too close to tol
     __shared__ R s_seg[32];
     __shared__ R s_act[32];
     __shared__ __align__(8) uint64_t s_mbar;
@@ -564,6 +590,13 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
     const bool lef = has_tile && j0 == 1, rig = has_tile && j0 + TJ - 1 == NY;
     const R w_has = has_tile ? R(1) : R(0);
     const R w_top = top ? R(2) : R(1), w_bot = bot ? R(2) : R(1), w_lef = lef ? R(1) : R(0), w_rig = rig ? R(1) : R(0);
+    // Halo offsets of the Jacobi sweeps.  All ghost cells of phi are Neumann copies of the wall-adjacent cell
+    // (rayleigh.py:436-445), so a wall tile reads that cell — its own edge row / column in the exchange plane —
+    // instead of a ghost: no ghost cell of phi is ever stored (30 predicated stores per thread and sweep, ~10
+    // shared-memory wavefronts per warp and sweep, gone).  Threads without a tile shadow tile 0.
+    const int tix = has_tile ? ti : 0, tjx = has_tile ? tj : 0;
+    const int o_n = tix == 0 ? 0 : -LDP, o_s = tix == NX / TI - 1 ? (TI - 1) * LDP : TI * LDP;
+    const int o_w = tjx == 0 ? 0 : -1, o_e = tjx == TILES_J - 1 ? TJ - 1 : TJ;
 #define TILE_LOOP                                      \
     _Pragma("unroll") for (int r = 0; r < TI; r++)     \
     _Pragma("unroll") for (int k = 0; k < TJ; k++)
@@ -701,28 +734,49 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
             // converged solve drops the two speculative sweeps and re-reads its tile of phi_{k-2}
             // from the exchange plane that still holds it, so the sweep count and the result are
             // exactly those of the reference's `while err > tol` loop.
+            // The reduction itself runs in fp32 (5 SHFL + 2 LDS.128 + 7 FADD per sweep instead of 10 SHFL +
+            // 8 LDS.64 + 12 DADD): its only use is the comparison with tol, and an fp32 sum of 256 positive
+            // terms is within ~1e-6 of the fp64 one.  Whenever the fp32 total lies within 1e-4 tol of tol
+            // (a few solves in a thousand) the decision is retaken from the per-thread fp64 residuals of
+            // that sweep, kept in a register, with the fp64 butterfly + pairwise tree: the stop test is
+            // decided by fp64 arithmetic in every case where fp32 could have changed it.
             R cn[TI][TJ], phi[TI][TJ];
             R *const pa = PA + opx, *const pb = PB + opx;
             auto tile_acc = [&](const R (&rs)[TI], const R (&dl)[TI], const R (&dr)[TI]) -> R {
                 // residual over the ghost-inclusive array: ghost copies re-count the wall-adjacent cells
-                R cl = dl[0] * dl[0], cr = dr[0] * dr[0], mid = R(0);
+                R cl = dl[0] * dl[0], cr = dr[0] * dr[0];
 #pragma unroll
                 for (int r = 1; r < TI; r++) { cl = fma(dl[r], dl[r], cl); cr = fma(dr[r], dr[r], cr); }
+#ifdef MAC_ACC_PRED
+                // wall contributions added under the tile's own wall predicates (no per-thread weight registers:
+                // under the 128-register cap the compiler re-derived those from tid in every sweep)
+                R acc = rs[0];
+#pragma unroll
+                for (int r = 1; r < TI; r++) acc += rs[r];
+                if (top) acc += rs[0];
+                if (bot) acc += rs[TI - 1];
+                if (lef) acc += cl;
+                if (rig) acc += cr;
+                return has_tile ? acc : R(0);
+#else
+                R mid = R(0);
 #pragma unroll
                 for (int r = 1; r < TI - 1; r++) mid += rs[r];
                 R acc = (TI > 1) ? fma(rs[0], w_top, fma(rs[TI - 1], w_bot, mid)) : rs[0] * (w_top + w_bot - R(1));
-                return fma(cl, w_lef, fma(cr, w_rig, acc));
+                return fma(cl, w_lef, fma(cr, w_rig, acc)) * w_has;
+#endif
             };
             // one sweep (every thread; threads without a tile work on tile 0's addresses and weigh 0)
             // + the warp reduction of the previous sweep's residual, one stage per column
-            auto sweep = [&](R (&ph)[TI][TJ], const R *pi, R &wsum) -> R {
+            auto sweep = [&](R (&ph)[TI][TJ], const R *pi, float &wsum) -> R {
                 // in place, column by column: the old values of column k-1 are kept in `po_`, column k+1
                 // is still old when column k is computed (one register tile, no copies)
-                R hn[TJ], hs[TJ], hw[TI], he[TI];    // halo: rows i0-1 / i0+TI, columns j0-1 / j0+TJ
+                R hn[TJ], hs[TJ], hw[TI], he[TI];    // halo: rows i0-1 / i0+TI, columns j0-1 / j0+TJ (wall tiles: their own edge)
+                const R *pn = pi + o_n, *ps = pi + o_s, *pw = pi + o_w, *pe = pi + o_e;
 #pragma unroll
-                for (int k = 0; k < TJ; k++) { hn[k] = pi[-LDP + k]; hs[k] = pi[TI * LDP + k]; }
+                for (int k = 0; k < TJ; k++) { hn[k] = pn[k]; hs[k] = ps[k]; }
 #pragma unroll
-                for (int r = 0; r < TI; r++) { hw[r] = pi[r * LDP - 1]; he[r] = pi[r * LDP + TJ]; }
+                for (int r = 0; r < TI; r++) { hw[r] = pw[r * LDP]; he[r] = pe[r * LDP]; }
                 R rs[TI], dl[TI], dr[TI], po_[TI];
 #pragma unroll
                 for (int r = 0; r < TI; r++) { rs[r] = R(0); po_[r] = hw[r]; }
@@ -750,37 +804,31 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
                 return tile_acc(rs, dl, dr);
             };
             auto commit = [&](const R (&nw)[TI][TJ], R *po) {
-                if (has_tile) {
-                    TILE_LOOP { po[r * LDP + k] = nw[r][k]; }
-                    if (top) {
-#pragma unroll
-                        for (int k = 0; k < TJ; k++) po[-LDP + k] = nw[0][k];
-                    }
-                    if (bot) {
-#pragma unroll
-                        for (int k = 0; k < TJ; k++) po[TI * LDP + k] = nw[TI - 1][k];
-                    }
-                    if (lef) {
-#pragma unroll
-                        for (int r = 0; r < TI; r++) po[r * LDP - 1] = nw[r][0];
-                    }
-                    if (rig) {
-#pragma unroll
-                        for (int r = 0; r < TI; r++) po[r * LDP + TJ] = nw[r][TJ - 1];
-                    }
-                }
+                if (has_tile) { TILE_LOOP { po[r * LDP + k] = nw[r][k]; } }
             };
-            auto total = [&](const R *part) -> R {   // same pairwise order in every thread -> uniform decision
-                R q[NW];
+            auto total32 = [&](const float *part) -> float {   // same pairwise order in every thread -> uniform decision
+                static_assert(NW % 4 == 0, "warp partials are read as float4");
+                float q[NW];
 #pragma unroll
-                for (int w = 0; w < NW; w++) q[w] = part[w];
+                for (int w = 0; w < NW; w += 4) {
+                    const float4 v = *reinterpret_cast<const float4 *>(part + w);
+                    q[w] = v.x; q[w + 1] = v.y; q[w + 2] = v.z; q[w + 3] = v.w;
+                }
 #pragma unroll
                 for (int st = 1; st < NW; st *= 2)
 #pragma unroll
                     for (int w = 0; w + st < NW; w += 2 * st) q[w] += q[w + st];
                 return q[0];
             };
-            R accp;                                       // residual of the last committed sweep (this thread)
+            const float tolf = (float)a.tol, tol_band = 1.0e-4f * (float)a.tol;
+            // `while err > tol` for one sweep: fp32 total when it is clearly on one side of tol, else the fp64 total of
+            // the per-thread residuals `mine` of that sweep (butterfly + pairwise tree, the order of the fp64-only code).
+            // The branch is uniform (every thread holds the same fp32 total); a NaN total takes the fp64 path.
+            auto converged = [&](const float err32, const R mine) -> bool {
+                if (fabsf(err32 - tolf) > tol_band) return !(err32 > tolf);
+                return residual_converged_exact<R, NW>(mine, s_exact, a.tol);      // cold, out of line
+            };
+            R accp, accq = R(0);                          // residuals (this thread) of the last committed sweep and of the one before
             // sweep 1 starts from phi = 0: phi_1 = cn, no halo reads
             {
                 R rs[TI], dl[TI], dr[TI];
@@ -801,46 +849,46 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
                         if (k == TJ - 1) dr[r] = cv;
                     }
                 }
-                accp = tile_acc(rs, dl, dr) * w_has;
+                accp = tile_acc(rs, dl, dr);
                 commit(phi, pb);
                 __syncthreads();
             }
             // sweep 2 (speculative until sweep 1's residual is known, two barriers from now)
             {
-                R ws = accp;
-                const R acc = sweep(phi, pb, ws) * w_has;
+                float ws = (float)accp;
+                const R acc = sweep(phi, pb, ws);
                 commit(phi, pa);
                 if ((tid & 31) == 0) s_part[1][tid >> 5] = ws;
                 __syncthreads();
-                accp = acc;
+                accq = accp; accp = acc;
             }
             int itp;
             const R *pf;                                  // plane holding the final iterate (tile-relative)
             for (int k = 3;; k += 2) {
                 {   // odd k: phi_{k-1} (in PA) -> phi_k; decide on sweep k-2 (still in PB)
-                    R ws = accp;
-                    const R acc = sweep(phi, pa, ws) * w_has;
-                    const R err = total(s_part[1]);
+                    float ws = (float)accp;
+                    const R acc = sweep(phi, pa, ws);
+                    const float err = total32(s_part[1]);
                     if (k - 2 > a.itmax) { status |= BEACON_STATUS_POISSON_OVERFLOW; itp = k - 2; pf = pb; break; }
-                    if (!(err > a.tol)) { itp = k - 2; pf = pb; break; }
+                    if (converged(err, accq)) { itp = k - 2; pf = pb; break; }
                     commit(phi, pb);
                     if ((tid & 31) == 0) s_part[0][tid >> 5] = ws;
                     __syncthreads();
-                    accp = acc;
+                    accq = accp; accp = acc;
                 }
                 {   // even k+1: phi_k (in PB) -> phi_{k+1}; decide on sweep k-1 (still in PA)
-                    R ws = accp;
-                    const R acc = sweep(phi, pb, ws) * w_has;
-                    const R err = total(s_part[0]);
+                    float ws = (float)accp;
+                    const R acc = sweep(phi, pb, ws);
+                    const float err = total32(s_part[0]);
                     if (k - 1 > a.itmax) { status |= BEACON_STATUS_POISSON_OVERFLOW; itp = k - 1; pf = pa; break; }
-                    if (!(err > a.tol)) { itp = k - 1; pf = pa; break; }
+                    if (converged(err, accq)) { itp = k - 1; pf = pa; break; }
                     commit(phi, pa);
                     if ((tid & 31) == 0) s_part[1][tid >> 5] = ws;
                     __syncthreads();
-                    accp = acc;
+                    accq = accp; accp = acc;
                 }
             }
-            TILE_LOOP { phi[r][k] = pf[r * LDP + k]; }     // the converged iterate (its ghosts are in the plane too)
+            TILE_LOOP { phi[r][k] = pf[r * LDP + k]; }     // the converged iterate
             it_total += itp;
             PHASE(2);
 
@@ -1061,15 +1109,17 @@ __global__ void __launch_bounds__(T, MINB) mac_big_kernel(const MacArgs<R> a)
 {
     constexpr int LD = NY + 2, N = (NX + 2) * LD;
     constexpr int LDP = ((LD + 6) / 8) * 8 + 1;         // exchange planes: stride = 1 mod 8
-    constexpr int NP = (NX + 2) * LDP;
+    constexpr int NP = ((NX + 2) * LDP + 3) / 4 * 4;    // plane size: a multiple of 16 bytes for fp32 too (PB is a bulk-copy destination)
     constexpr int TILES_J = NY / TJ, TILES = (NX / TI) * TILES_J, NW = T / 32;
     constexpr int RS = wavefront_row_stride(NY);        // wavefront planes: columns 0..NY per row pair, padded
     constexpr int PASS_ROWS = ((NX / 2 + TI - 1) / TI) * TI >= 64 ? 64 / TI * TI : ((NX / 2 + TI - 1) / TI) * TI;   // rows per transport pass
     constexpr int PASSES = (NX + PASS_ROWS - 1) / PASS_ROWS, LANES_MAX = PASS_ROWS / 2;
     static_assert(NX % TI == 0 && NY % TJ == 0 && TILES <= T && TI % 2 == 0, "tiles must cover the grid exactly");
+    static_assert((NP * sizeof(R)) % 16 == 0, "bulk copies need 16-byte aligned planes");
     static_assert(LANES_MAX <= 32 && 3 * (LANES_MAX * RS + 8) * 2 <= 2 * NP, "transport planes must fit the exchange planes");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ __align__(16) R s_part[2][NW];
+    __shared__ __align__(16) float s_part[2][NW];     // fp32 warp partials of the residual (see mac_reg_kernel)
+    __shared__ R s_exact[NW];                         // fp64 warp partials, only when the fp32 total is too close to tol
     __shared__ __align__(8) uint64_t s_mbar;
     __shared__ R s_red[NW];
     __shared__ R s_seg[128];
@@ -1100,6 +1150,13 @@ __global__ void __launch_bounds__(T, MINB) mac_big_kernel(const MacArgs<R> a)
     const R w_has = has_tile ? R(1) : R(0);
     // residual weights: ghost copies re-count wall-adjacent cells; mixing's j = NY+1 ghost is Dirichlet 0 (mixing.py:451)
     const R w_top = top ? R(2) : R(1), w_bot = bot ? R(2) : R(1), w_lef = lef ? R(1) : R(0), w_rig = (rig && ray) ? R(1) : R(0);
+    // Halo offsets of the Jacobi sweeps: a Neumann ghost is a copy of the wall-adjacent cell, so wall tiles read
+    // their own edge row / column instead (no ghost cell of phi is ever stored); mixing's Dirichlet ghost
+    // phi(i, NY+1) = 0 (mixing.py:451) is a constant.  Threads without a tile shadow tile 0.
+    const int tix = has_tile ? ti : 0, tjx = has_tile ? tj : 0;
+    const int o_n = tix == 0 ? 0 : -LDP, o_s = tix == NX / TI - 1 ? (TI - 1) * LDP : TI * LDP;
+    const int o_w = tjx == 0 ? 0 : -1, o_e = tjx == TILES_J - 1 ? TJ - 1 : TJ;
+    const bool dir_e = rig && !ray;
 #define TILE_LOOP                                      \
     _Pragma("unroll") for (int r = 0; r < TI; r++)     \
     _Pragma("unroll") for (int k = 0; k < TJ; k++)
@@ -1285,22 +1342,23 @@ __global__ void __launch_bounds__(T, MINB) mac_big_kernel(const MacArgs<R> a)
                 R acc = (TI > 1) ? fma(rs[0], w_top, fma(rs[TI - 1], w_bot, mid)) : rs[0] * (w_top + w_bot - R(1));
                 return fma(cl, w_lef, fma(cr, w_rig, acc));
             };
-            auto sweep = [&](R (&ph)[TI][TJ], const R *pi, R &wsum) -> R {
+            auto sweep = [&](R (&ph)[TI][TJ], const R *pi, float &wsum) -> R {
                 // in place, column by column; halo values are fetched where they are used (register budget)
                 R rs[TI], po_[TI], cl = R(0), cr = R(0);
+                const R *pn = pi + o_n, *ps = pi + o_s, *pw = pi + o_w, *pe = pi + o_e;
 #pragma unroll
-                for (int r = 0; r < TI; r++) { rs[r] = R(0); po_[r] = pi[r * LDP - 1]; }
+                for (int r = 0; r < TI; r++) { rs[r] = R(0); po_[r] = pw[r * LDP]; }
 #pragma unroll
                 for (int k = 0; k < TJ; k++) {
                     if (k < 5) wsum += __shfl_xor_sync(0xffffffffu, wsum, 16 >> k);
-                    const R hnk = pi[-LDP + k], hsk = pi[TI * LDP + k];
+                    const R hnk = pn[k], hsk = ps[k];
                     R old[TI];
 #pragma unroll
                     for (int r = 0; r < TI; r++) old[r] = ph[r][k];
 #pragma unroll
                     for (int r = 0; r < TI; r++) {
                         const R xm = (r > 0) ? old[r - 1] : hnk, xp = (r < TI - 1) ? old[r + 1] : hsk;
-                        const R ym = po_[r], yp = (k < TJ - 1) ? ph[r][k + 1] : pi[r * LDP + TJ];
+                        const R ym = po_[r], yp = (k < TJ - 1) ? ph[r][k + 1] : (dir_e ? R(0) : pe[r * LDP]);
                         const R nv = fma(xp + xm, a.pk1, fma(yp + ym, a.pk2, cn[r][k]));
                         const R d = nv - old[r];
                         rs[r] = fma(d, d, rs[r]);
@@ -1319,37 +1377,28 @@ __global__ void __launch_bounds__(T, MINB) mac_big_kernel(const MacArgs<R> a)
                 return fma(cl, w_lef, fma(cr, w_rig, acc));
             };
             auto commit = [&](const R (&nw)[TI][TJ], R *po) {
-                if (has_tile) {
-                    TILE_LOOP { po[r * LDP + k] = nw[r][k]; }
-                    if (top) {
+                if (has_tile) { TILE_LOOP { po[r * LDP + k] = nw[r][k]; } }
+            };
+            auto total32 = [&](const float *part) -> float {   // fixed pairwise order in every thread -> uniform decision
+                static_assert(NW % 4 == 0, "warp partials are read as float4");
+                float q[NW];
 #pragma unroll
-                        for (int k = 0; k < TJ; k++) po[-LDP + k] = nw[0][k];
-                    }
-                    if (bot) {
-#pragma unroll
-                        for (int k = 0; k < TJ; k++) po[TI * LDP + k] = nw[TI - 1][k];
-                    }
-                    if (lef) {
-#pragma unroll
-                        for (int r = 0; r < TI; r++) po[r * LDP - 1] = nw[r][0];
-                    }
-                    if (rig) {
-#pragma unroll
-                        for (int r = 0; r < TI; r++) po[r * LDP + TJ] = ray ? nw[r][TJ - 1] : R(0);
-                    }
+                for (int w = 0; w < NW; w += 4) {
+                    const float4 v = *reinterpret_cast<const float4 *>(part + w);
+                    q[w] = v.x; q[w + 1] = v.y; q[w + 2] = v.z; q[w + 3] = v.w;
                 }
+#pragma unroll
+                for (int st = 1; st < NW; st *= 2)
+#pragma unroll
+                    for (int w = 0; w + st < NW; w += 2 * st) q[w] += q[w + st];
+                return q[0];
             };
-            auto total = [&](const R *part) -> R {   // fixed pairwise order in every thread -> uniform decision
-                R t4[NW / 4];
-#pragma unroll
-                for (int g = 0; g < NW / 4; g++) t4[g] = (part[4 * g] + part[4 * g + 1]) + (part[4 * g + 2] + part[4 * g + 3]);
-#pragma unroll
-                for (int st = 1; st < NW / 4; st *= 2)
-#pragma unroll
-                    for (int w = 0; w + st < NW / 4; w += 2 * st) t4[w] += t4[w + st];
-                return t4[0];
+            const float tolf = (float)a.tol, tol_band = 1.0e-4f * (float)a.tol;
+            auto converged = [&](const float err32, const R mine) -> bool {   // see mac_reg_kernel
+                if (fabsf(err32 - tolf) > tol_band) return !(err32 > tolf);
+                return residual_converged_exact<R, NW>(mine, s_exact, a.tol);
             };
-            R accp;
+            R accp, accq = R(0);
             {   // sweep 1 starts from phi = 0: phi_1 = cn, no halo reads
                 R rs[TI], dl[TI], dr[TI];
 #pragma unroll
@@ -1368,40 +1417,40 @@ __global__ void __launch_bounds__(T, MINB) mac_big_kernel(const MacArgs<R> a)
                 __syncthreads();
             }
             {   // sweep 2
-                R ws = accp;
+                float ws = (float)accp;
                 const R acc = sweep(phi, pb, ws) * w_has;
                 commit(phi, pa);
                 if ((tid & 31) == 0) s_part[1][tid >> 5] = ws;
                 __syncthreads();
-                accp = acc;
+                accq = accp; accp = acc;
             }
             int itp;
             const R *pf;                                  // plane holding the final iterate (tile-relative)
             for (int k = 3;; k += 2) {
                 {   // odd k: phi_{k-1} (in PA) -> phi_k; decide on sweep k-2 (still in PB)
-                    R ws = accp;
+                    float ws = (float)accp;
                     const R acc = sweep(phi, pa, ws) * w_has;
-                    const R err = total(s_part[1]);
+                    const float err = total32(s_part[1]);
                     if (k - 2 > a.itmax) { status |= BEACON_STATUS_POISSON_OVERFLOW; itp = k - 2; pf = pb; break; }
-                    if (!(err > a.tol)) { itp = k - 2; pf = pb; break; }
+                    if (converged(err, accq)) { itp = k - 2; pf = pb; break; }
                     commit(phi, pb);
                     if ((tid & 31) == 0) s_part[0][tid >> 5] = ws;
                     __syncthreads();
-                    accp = acc;
+                    accq = accp; accp = acc;
                 }
                 {   // even k+1: phi_k (in PB) -> phi_{k+1}; decide on sweep k-1 (still in PA)
-                    R ws = accp;
+                    float ws = (float)accp;
                     const R acc = sweep(phi, pb, ws) * w_has;
-                    const R err = total(s_part[0]);
+                    const float err = total32(s_part[0]);
                     if (k - 1 > a.itmax) { status |= BEACON_STATUS_POISSON_OVERFLOW; itp = k - 1; pf = pa; break; }
-                    if (!(err > a.tol)) { itp = k - 1; pf = pa; break; }
+                    if (converged(err, accq)) { itp = k - 1; pf = pa; break; }
                     commit(phi, pa);
                     if ((tid & 31) == 0) s_part[1][tid >> 5] = ws;
                     __syncthreads();
-                    accp = acc;
+                    accq = accp; accp = acc;
                 }
             }
-            TILE_LOOP { phi[r][k] = pf[r * LDP + k]; }     // the converged iterate (its ghosts are in the plane too)
+            TILE_LOOP { phi[r][k] = pf[r * LDP + k]; }     // the converged iterate
             it_total += itp;
             PHASE(2);
 
@@ -1595,7 +1644,7 @@ public:
             if (getenv("BEACON_MAC_DEBUG")) kernel = mac_big_kernel<R, 100, 100, 4, 5, 512, 1, true>;
             else kernel = mac_big_kernel<R, 100, 100, 4, 5, 512, 1, false>;
             T = 512; TI = 4; TJ = 5; dbg_variant = true; big_variant = true;
-            smem = sizeof(R) * 2 * (size_t)102 * 105;
+            smem = sizeof(R) * 2 * (size_t)((102 * 105 + 3) / 4 * 4);
         } else if (2 * plane + 1024 <= 220 * 1024 && ((nx + 3) / 4) * ((ny + 4) / 5) <= 512) {
             kernel = mac_kernel<R, 4, 5, 512, false>; T = 512; TI = 4; TJ = 5; smem = 2 * plane;
         } else

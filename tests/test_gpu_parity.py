@@ -21,12 +21,17 @@ pytestmark = pytest.mark.gpu
 RTOL64 = 1e-10
 
 
-def close(a, b, rtol=RTOL64, what=""):
-    """Per-element relative tolerance with an absolute floor:
-        |a - b| <= rtol * |b| + 1e-3 * rtol * scale,     scale = max(1, max|b|)
-    i.e. every entry agrees to `rtol` relative to ITS OWN magnitude; entries below 1e-3 of the field
-    scale (zeros at walls, rhs entries that are differences of O(1) fluxes, u, v << 1) are held to an
-    absolute 1e-13 * scale in fp64.  Returns the largest scale-relative error."""
+def close(a, b, rtol=RTOL64, what="", floor=1e-2):
+    """The norm of every field comparison:
+        |a - b| <= rtol * (|b| + floor * scale),     scale = max(1, max|b|)
+    floor = 1e-2 (default, solution fields h, q, u, v, p, T, C, observations): every entry agrees to `rtol`
+    relative to ITS OWN magnitude, entries below 1 % of the field scale (zeros at walls, u, v << 1) are held to
+    an absolute 1e-12 * scale in fp64.
+    floor = 1 (right-hand sides rhsh / rhsq, and every fp32 comparison): relative to the field scale.  An rhsq
+    entry is a difference of stencil terms of magnitude ~750 (d3o2u divides O(1) differences by 2 dx^3 = 0.016):
+    its absolute rounding noise, in the reference as well, is ~1e-12 whatever the size of the result, so a
+    per-entry relative bound is not meaningful there; in fp32 one rounding is 6e-8 of the field scale.
+    Returns the largest scale-relative error."""
     a = np.asarray(a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     assert a.shape == b.shape, (what, a.shape, b.shape)
@@ -35,9 +40,9 @@ def close(a, b, rtol=RTOL64, what=""):
     scale = max(1.0, float(np.max(np.abs(b))))
     assert np.all(np.isfinite(a)), what
     err = np.abs(a - b)
-    lim = rtol * np.abs(b) + 1e-3 * rtol * scale
+    lim = rtol * (np.abs(b) + floor * scale)
     worst = int(np.argmax(err - lim))
-    assert np.all(err <= lim), (f"{what}: entry {worst}: |a-b| = {err.flat[worst]:.3e} > {rtol:.0e}*|b| + floor = {lim.flat[worst]:.3e} "
+    assert np.all(err <= lim), (f"{what}: entry {worst}: |a-b| = {err.flat[worst]:.3e} > {rtol:.0e}*(|b| + {floor:g} scale) = {lim.flat[worst]:.3e} "
                                f"(b = {b.flat[worst]:.6e}, scale {scale:.3g})")
     return float(np.max(err)) / scale
 
@@ -62,7 +67,7 @@ def test_shkadov_golden(golden, tag, n_jets):
     for k in range(g[f"{tag}_actions"].shape[0]):
         obs, rwd, done, trunc = env.step(rep(g[f"{tag}_actions"][k], B), noise=rep(g[f"{tag}_noise"][k], B))
         for f in ("h", "q", "rhsh", "rhsq"):
-            close(env.get_state(f), rep(g[f"{tag}_{f}"][k], B), what=f"{f} step {k}")
+            close(env.get_state(f), rep(g[f"{tag}_{f}"][k], B), what=f"{f} step {k}", floor=1.0 if f.startswith("rhs") else 1e-2)
         close(obs, rep(g[f"{tag}_obs"][k], B), what="obs")
         close(rwd, rep(g[f"{tag}_rwd"][k], B), rtol=1e-12, what="rwd")
         assert not done.any() and not trunc.any()
@@ -116,7 +121,7 @@ def test_shkadov_vs_oracle_resync():
         obs, rwd, done, trunc = env.step(torch.as_tensor(acts), noise=torch.as_tensor(noise))
         ref = [o.step(acts[b], noise=noise[b]) for b, o in enumerate(orcs)]
         for f in ("h", "q", "rhsh", "rhsq"):
-            close(env.get_state(f), np.stack([getattr(o, f) for o in orcs]), what=f"{f} action {k}")
+            close(env.get_state(f), np.stack([getattr(o, f) for o in orcs]), what=f"{f} action {k}", floor=1.0 if f.startswith("rhs") else 1e-2)
         close(obs, np.stack([r[0] for r in ref]), what="obs")
         close(rwd, np.array([r[1] for r in ref]), rtol=1e-12, what="rwd")
 
@@ -146,7 +151,7 @@ def test_shkadov_general_paths_vs_oracle(kw, noalign, monkeypatch):
         obs, rwd, done, trunc = env.step(torch.as_tensor(acts), noise=torch.as_tensor(noise))
         ref = [o.step(acts[b], noise=noise[b]) for b, o in enumerate(orcs)]
         for f in ("h", "q", "rhsh", "rhsq"):
-            close(env.get_state(f), np.stack([getattr(o, f) for o in orcs]), what=f"{f} action {k}")
+            close(env.get_state(f), np.stack([getattr(o, f) for o in orcs]), what=f"{f} action {k}", floor=1.0 if f.startswith("rhs") else 1e-2)
         close(obs, np.stack([r[0] for r in ref]), what="obs")
         close(rwd, np.array([r[1] for r in ref]), rtol=1e-12, what="rwd")
 
@@ -278,7 +283,7 @@ def test_sloshing_golden(golden):
     for k in range(g["actions"].shape[0]):
         obs, rwd, d, t = env.step(rep(g["actions"][k], B))
         for f in ("h", "q", "rhsh", "rhsq"):
-            close(env.get_state(f), rep(g[f][k], B), what=f"{f} step {k}")
+            close(env.get_state(f), rep(g[f][k], B), what=f"{f} step {k}", floor=1.0 if f.startswith("rhs") else 1e-2)
         close(obs, rep(g["obs"][k], B), what="obs")
         close(rwd, rep(g["rwd"][k], B), rtol=1e-12, what="rwd")
 
@@ -385,13 +390,13 @@ def test_fp32_tolerance(golden):
     env = make("shkadov", 2, n_jets=10, dtype=torch.float32)
     env.reset()
     env.step(rep(g["j10_actions"][0], 2), noise=rep(g["j10_noise"][0], 2))
-    close(env.get_state("h"), rep(g["j10_h"][0], 2), rtol=1e-5, what="h fp32")
-    close(env.get_state("q"), rep(g["j10_q"][0], 2), rtol=1e-5, what="q fp32")
+    close(env.get_state("h"), rep(g["j10_h"][0], 2), rtol=1e-5, what="h fp32", floor=1.0)
+    close(env.get_state("q"), rep(g["j10_q"][0], 2), rtol=1e-5, what="q fp32", floor=1.0)
     g = golden("sloshing")
     env = make("sloshing", 2, dtype=torch.float32)
     env.reset()
     env.step(rep(g["actions"][0], 2))
-    close(env.get_state("h"), rep(g["h"][0], 2), rtol=1e-5, what="sloshing h fp32")
+    close(env.get_state("h"), rep(g["h"][0], 2), rtol=1e-5, what="sloshing h fp32", floor=1.0)
 
 
 def test_capi_errors_are_reported():

@@ -20,8 +20,8 @@ def test_fp32_burgers_one_action(golden):
     env = make("burgers", 2, dtype=torch.float32)
     env.reset()
     obs, rwd, d, t = env.step(rep(g["actions"][0], 2).float(), noise=rep(g["noise"][0:1], 2).float())
-    close(env.get_state("u"), rep(g["u"][0], 2), rtol=RTOL32, what="burgers u fp32")
-    close(obs, rep(g["obs"][0], 2), rtol=RTOL32, what="burgers obs fp32")
+    close(env.get_state("u"), rep(g["u"][0], 2), rtol=RTOL32, what="burgers u fp32", floor=1.0)
+    close(obs, rep(g["obs"][0], 2), rtol=RTOL32, what="burgers obs fp32", floor=1.0)
     assert abs(float(rwd[0]) - float(g["rwd"][0])) <= RTOL32 * max(1.0, abs(float(g["rwd"][0])))
 
 
@@ -30,13 +30,13 @@ def test_fp32_lorenz_vortex_one_action(golden):
     env = make("lorenz", 2, dtype=torch.float32)
     env.reset()
     obs, rwd, d, t = env.step(torch.full((2,), int(g["actions"][0])))
-    close(obs, rep(g["obs"][0], 2), rtol=RTOL32, what="lorenz obs fp32")
-    close(env.get_state("x"), rep(g["x"][0], 2), rtol=RTOL32, what="lorenz x fp32")
+    close(obs, rep(g["obs"][0], 2), rtol=RTOL32, what="lorenz obs fp32", floor=1.0)
+    close(env.get_state("x"), rep(g["x"][0], 2), rtol=RTOL32, what="lorenz x fp32", floor=1.0)
     g = golden("vortex")
     env = make("vortex", 2, dtype=torch.float32)
     env.reset()
     obs, rwd, d, t = env.step(rep(g["actions"][0], 2).float())
-    close(env.get_state("x"), rep(g["x"][0], 2), rtol=RTOL32, what="vortex x fp32")
+    close(env.get_state("x"), rep(g["x"][0], 2), rtol=RTOL32, what="vortex x fp32", floor=1.0)
 
 
 @pytest.mark.timeout(900)
@@ -59,8 +59,8 @@ def test_fp32_mac2d_one_action(golden, name, scal, k):
     it, it_ref = int(env.last_iters[0, 0]), int(g["itp"][k].sum())
     assert abs(it - it_ref) <= 0.05 * it_ref, (it, it_ref)
     for f in ("u", "v", scal):
-        close(env.get_state(f), rep(g[f][k].reshape(-1), B), rtol=RTOL32, what=f"{name} {f} fp32")
-    close(obs, rep(g["obs"][k], B), rtol=RTOL32, what="obs fp32")
+        close(env.get_state(f), rep(g[f][k].reshape(-1), B), rtol=RTOL32, what=f"{name} {f} fp32", floor=1.0)
+    close(obs, rep(g["obs"][k], B), rtol=RTOL32, what="obs fp32", floor=1.0)
 
 
 # ----------------------------------------------------------------------------- whole-episode returns and fields (§8c)
@@ -184,10 +184,14 @@ def test_state_dict_carries_the_noise_stream(name, kw, adim):
     b.load_state_dict(sd)
     oa, ob = a.step_fused(acts[2:]), b.step_fused(acts[2:])
     assert all(torch.equal(x, y) for x, y in zip(oa, ob))
-    c = make(name, 3, seed=42, **kw)                        # without the counter the stream restarts: results differ
+    # the inlet noise has not reached the probes after two actions: compare the whole lattice
+    fld = "h" if name == "shkadov" else "u"
+    assert torch.equal(a.get_state(fld), b.get_state(fld)) and torch.equal(a.get_state("draws"), b.get_state("draws"))
+    c = make(name, 3, seed=42, **kw)                        # without the counter the stream restarts: the inlet differs
     c.reset()
     c.load_state_dict({k: v for k, v in sd.items() if k != "draws"})
-    assert not torch.equal(c.step_fused(acts[2:])[0], oa[0])
+    c.step_fused(acts[2:])
+    assert not torch.equal(c.get_state(fld), a.get_state(fld))
 
 
 def test_step_host_validates_buffers():
