@@ -30,6 +30,7 @@
 //     the new west value travelling by warp shuffle (no barriers).
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <type_traits>
 
 #include "common.cuh"
@@ -557,11 +558,15 @@ __device__ __noinline__ bool residual_converged_exact(R mine, R *s_exact, R tol)
 //     software-pipelined pass (coefficients of column j+1 are loaded while column j waits for
 //     the shuffle), critical path per column = SHFL + 2 FMA.
 // ---------------------------------------------------------------------------------------
+// Row stride of the exchange planes: with ten tiles per tile row (TJ = 5, tid = 10 ti + tj) the tile origins of a
+// half-warp fall into 16 distinct 8-byte banks iff (TI * LDP) mod 16 == 2 (TI = 2: 57, TI = 5: 58).
+constexpr int mac_ldp(int ld, int ti) { int l = ld; while ((ti * l) % 16 != 2) l++; return l; }
+
 template <typename R, int NX, int NY, int TI, int TJ, int T, bool DBG>
 __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
 {
     constexpr int LD = NY + 2, N = (NX + 2) * LD;       // field planes
-    constexpr int LDP = ((LD + 6) / 8) * 8 + 1;         // exchange planes: stride = 1 mod 8
+    constexpr int LDP = mac_ldp(LD, TI);                // exchange planes: conflict-free stride
     constexpr int NP = (NX + 2) * LDP;
     constexpr int TILES_J = NY / TJ, TILES = (NX / TI) * TILES_J, NW = T / 32;
     static_assert(NX % TI == 0 && NY % TJ == 0 && TILES <= T, "tiles must cover the grid exactly");
@@ -596,7 +601,6 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
     // shared-memory wavefronts per warp and sweep, gone).  Threads without a tile shadow tile 0.
     const int tix = has_tile ? ti : 0, tjx = has_tile ? tj : 0;
     const int o_n = tix == 0 ? 0 : -LDP, o_s = tix == NX / TI - 1 ? (TI - 1) * LDP : TI * LDP;
-    const int o_w = tjx == 0 ? 0 : -1, o_e = tjx == TILES_J - 1 ? TJ - 1 : TJ;
 #define TILE_LOOP                                      \
     _Pragma("unroll") for (int r = 0; r < TI; r++)     \
     _Pragma("unroll") for (int k = 0; k < TJ; k++)
@@ -747,24 +751,11 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
                 R cl = dl[0] * dl[0], cr = dr[0] * dr[0];
 #pragma unroll
                 for (int r = 1; r < TI; r++) { cl = fma(dl[r], dl[r], cl); cr = fma(dr[r], dr[r], cr); }
-#ifdef MAC_ACC_PRED
-                // wall contributions added under the tile's own wall predicates (no per-thread weight registers:
-                // under the 128-register cap the compiler re-derived those from tid in every sweep)
-                R acc = rs[0];
-#pragma unroll
-                for (int r = 1; r < TI; r++) acc += rs[r];
-                if (top) acc += rs[0];
-                if (bot) acc += rs[TI - 1];
-                if (lef) acc += cl;
-                if (rig) acc += cr;
-                return has_tile ? acc : R(0);
-#else
                 R mid = R(0);
 #pragma unroll
                 for (int r = 1; r < TI - 1; r++) mid += rs[r];
                 R acc = (TI > 1) ? fma(rs[0], w_top, fma(rs[TI - 1], w_bot, mid)) : rs[0] * (w_top + w_bot - R(1));
                 return fma(cl, w_lef, fma(cr, w_rig, acc)) * w_has;
-#endif
             };
             // one sweep (every thread; threads without a tile work on tile 0's addresses and weigh 0)
             // + the warp reduction of the previous sweep's residual, one stage per column
@@ -772,14 +763,18 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
                 // in place, column by column: the old values of column k-1 are kept in `po_`, column k+1
                 // is still old when column k is computed (one register tile, no copies)
                 R hn[TJ], hs[TJ], hw[TI], he[TI];    // halo: rows i0-1 / i0+TI, columns j0-1 / j0+TJ (wall tiles: their own edge)
-                const R *pn = pi + o_n, *ps = pi + o_s, *pw = pi + o_w, *pe = pi + o_e;
+                const R *pn = pi + o_n, *ps = pi + o_s;
 #pragma unroll
                 for (int k = 0; k < TJ; k++) { hn[k] = pn[k]; hs[k] = ps[k]; }
+                // west / east: every lane loads at the same tile-relative offset (conflict free; clamped offsets would put
+                // the lanes of wall tiles one bank off the others: 2-way conflicts in every warp, measured -3.7 %) and
+                // wall tiles take their own edge column from registers instead
+                const bool lefx = tjx == 0, rigx = tjx == TILES_J - 1;
 #pragma unroll
-                for (int r = 0; r < TI; r++) { hw[r] = pw[r * LDP]; he[r] = pe[r * LDP]; }
+                for (int r = 0; r < TI; r++) { hw[r] = pi[r * LDP - 1]; he[r] = pi[r * LDP + TJ]; }
                 R rs[TI], dl[TI], dr[TI], po_[TI];
 #pragma unroll
-                for (int r = 0; r < TI; r++) { rs[r] = R(0); po_[r] = hw[r]; }
+                for (int r = 0; r < TI; r++) { rs[r] = R(0); po_[r] = lefx ? ph[r][0] : hw[r]; he[r] = rigx ? ph[r][TJ - 1] : he[r]; }
 #pragma unroll
                 for (int k = 0; k < TJ; k++) {
                     if (k < 5) wsum += __shfl_xor_sync(0xffffffffu, wsum, 16 >> k);
@@ -912,12 +907,11 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
             // west ghost row (i = 0, never updated) is folded into A of row 1 (B_W := 0 there).
             {
                 constexpr int RS = wavefront_row_stride(NY);       // columns 0..NY per row pair (0 unused), padded
-                static_assert(TI == 2 && NX % 2 == 0 && NX / 2 <= 32, "wavefront layout: one tile row = one lane's row pair");
+                static_assert(NX % 2 == 0 && NX / 2 <= 32, "wavefront layout: one lane per row pair");
                 static_assert(2 * (NX / 2) * RS <= NP, "wavefront planes must fit the exchange planes");
                 const R kx = a.tcoef * a.inv_dx2, ky = a.tcoef * a.inv_dy2;
                 if (has_tile) {
                     const R *u = U + o, *v = V + o, *sc = S + o;
-                    R *AAw = PA + (size_t)(ti * RS + j0) * 2, *WWw = PB + (size_t)(ti * RS + j0) * 2;
                     TILE_LOOP {
                         const int e = r * LD + k;
                         const R uE = u[e + LD], uW = u[e], vN = v[e + 1], vS = v[e];
@@ -927,8 +921,9 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
                         R A = s0 + dt * (diff0 - conv0);
                         R BW = dt * (kx + R(0.5) * uW * inv_dx);
                         if (r == 0 && top) { A = fma(BW, sc[e - LD], A); BW = R(0); }
-                        AAw[k * 2 + r] = A;
-                        WWw[k * 2 + r] = BW;
+                        const int gi = TI * ti + r, idx = ((gi >> 1) * RS + j0 + k) * 2 + (gi & 1);   // [row pair][column][row in pair]
+                        PA[idx] = A;
+                        PB[idx] = BW;
                     }
                 }
                 __syncthreads();
@@ -1635,10 +1630,16 @@ public:
         reg_variant = false;
         if (ray && nx == 50 && ny == 50 && sizeof(R) * (2 * 52 * 57 + 3 * 52 * 52) <= 113 * 1024 && p.n_sgts <= 32 && !getenv("BEACON_MAC_V1")) {
             // five planes fit twice per SM: register-resident phi tiles, 2 CTAs/SM
-            if (getenv("BEACON_MAC_DEBUG")) kernel = mac_reg_kernel<R, 50, 50, 2, 5, 256, true>;
-            else kernel = mac_reg_kernel<R, 50, 50, 2, 5, 256, false>;
-            T = 256; TI = 2; TJ = 5;
-            smem = sizeof(R) * (2 * 52 * 57 + 3 * 52 * 52); reg_variant = true; dbg_variant = true;
+            const char *tile = getenv("BEACON_MAC_TILE");              // tuning: "5x5" = 100 threads with 25 cells each
+            if (tile && !strcmp(tile, "5x5")) {
+                kernel = mac_reg_kernel<R, 50, 50, 5, 5, 128, false>;
+                T = 128; TI = 5; TJ = 5;
+            } else {
+                if (getenv("BEACON_MAC_DEBUG")) kernel = mac_reg_kernel<R, 50, 50, 2, 5, 256, true>;
+                else kernel = mac_reg_kernel<R, 50, 50, 2, 5, 256, false>;
+                T = 256; TI = 2; TJ = 5; dbg_variant = true;
+            }
+            smem = sizeof(R) * (2 * 52 * mac_ldp(52, TI) + 3 * 52 * 52); reg_variant = true;
         } else if (nx == 100 && ny == 100 && !getenv("BEACON_MAC_V1")) {
             // register-resident Poisson, fields in L2: one CTA of 500 tile threads per SM
             if (getenv("BEACON_MAC_DEBUG")) kernel = mac_big_kernel<R, 100, 100, 4, 5, 512, 1, true>;
