@@ -449,6 +449,10 @@ __global__ void __launch_bounds__(T) mac_kernel(const MacArgs<R> a)
 // SHFL + 2 DFMA; coefficients are fetched two columns ahead.  A separate (noinline) function so
 // that its register allocation is independent of the big per-env kernel around it.
 // ---------------------------------------------------------------------------------------
+template <typename R> struct vec2_of;
+template <> struct vec2_of<double> { typedef double2 type; };
+template <> struct vec2_of<float> { typedef float2 type; };
+
 __device__ __forceinline__ double2 lds128_f64(uint32_t a)
 {
     double2 v;
@@ -462,39 +466,40 @@ __device__ __forceinline__ double lds64_f64(uint32_t a)
     return v;
 }
 
-template <int NX, int NY, int LD>
-__device__ __noinline__ void transport_wavefront_f64(uint32_t sAA, uint32_t sWW, uint32_t sV, uint32_t sS, double hk, double dky, int lane)
+template <int NX, int NY, int LDU, int LDT>
+__device__ __noinline__ void transport_wavefront_f64(uint32_t sAA, uint32_t sWW, uint32_t sUV, uint32_t sS, double hk, double dky, int lane)
 {
+    // sUV: plane of (u, v) pairs, row stride LDU pairs (v = second component); sS: scalar plane, row stride LDT
     constexpr int LANES = NX / 2, STEPS = NY + LANES - 1, RS = wavefront_row_stride(NY);
     const bool on = lane < LANES;
     const int l = on ? lane : 0;                       // lanes beyond the last row pair mimic lane 0, predicate off
-    const uint32_t rowA = (uint32_t)(l * RS) * 16u, rowV = (uint32_t)((2 * l + 1) * LD) * 8u;
+    const uint32_t rowA = (uint32_t)(l * RS) * 16u, rowV = (uint32_t)((2 * l + 1) * LDU) * 16u + 8u, rowS = (uint32_t)((2 * l + 1) * LDT) * 8u;
     // column 1: partial sums with the south ghost (column 0, untouched by transport)
     const double2 a1 = lds128_f64(sAA + rowA + 16u), w1c = lds128_f64(sWW + rowA + 16u);
-    double p0 = fma(fma(hk, lds64_f64(sV + rowV + 8u), dky), lds64_f64(sS + rowV), a1.x);
-    double p1 = fma(fma(hk, lds64_f64(sV + rowV + LD * 8u + 8u), dky), lds64_f64(sS + rowV + LD * 8u), a1.y);
+    double p0 = fma(fma(hk, lds64_f64(sUV + rowV + 16u), dky), lds64_f64(sS + rowS), a1.x);
+    double p1 = fma(fma(hk, lds64_f64(sUV + rowV + LDU * 16u + 16u), dky), lds64_f64(sS + rowS + LDT * 8u), a1.y);
     double w0 = w1c.x, w1 = w1c.y;
     // bases biased by -lane: element [t] is column t - l + 2 (coefficients) / t - l + 1 (store)
     const uint32_t aA = sAA + rowA + (uint32_t)(2 - l) * 16u, aW = sWW + rowA + (uint32_t)(2 - l) * 16u;
-    const uint32_t aV = sV + rowV + (uint32_t)(2 - l) * 8u;
+    const uint32_t aV = sUV + rowV + (uint32_t)(2 - l) * 16u;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // store pointers: S plane rows 2l+1, 2l+2, biased so that element [t] is column t - l + 1
-    double *S0o = reinterpret_cast<double *>(smem_raw + (sS - (uint32_t)__cvta_generic_to_shared(smem_raw)) + rowV) + (1 - l), *S1o = S0o + LD;
+    double *S0o = reinterpret_cast<double *>(smem_raw + (sS - (uint32_t)__cvta_generic_to_shared(smem_raw)) + rowS) + (1 - l), *S1o = S0o + LDT;
     double2 an = lds128_f64(aA), wn = lds128_f64(aW);
-    double v0n = lds64_f64(aV), v1n = lds64_f64(aV + LD * 8u);
+    double v0n = lds64_f64(aV), v1n = lds64_f64(aV + LDU * 16u);
     double last_new = 0.0;
     const int c0 = on ? -lane : -(1 << 20);
     // unrolled by 6 so that the three column records in flight rotate through registers without
     // copies; the trip count is padded to a multiple of 6 (the extra steps are inactive, their
     // reads stay inside the planes)
     constexpr int STEPS_PAD = ((STEPS + 5) / 6) * 6;
-    static_assert(((NX / 2 - 1) * RS + 2 - (NX / 2 - 1) + STEPS_PAD + 1) * 2 <= (NX + 2) * (((NY + 2 + 6) / 8) * 8 + 1), "padded reads leave the A/W planes");
-    static_assert((NX - 1) * LD + 2 - (NX / 2 - 1) + STEPS_PAD + 1 + LD <= (NX + 2) * LD, "padded reads leave the V plane");
+    static_assert(((NX / 2 - 1) * RS + 2 - (NX / 2 - 1) + STEPS_PAD + 1) * 2 <= (NX + 1) * (((NY + 2 + 6) / 8) * 8 + 1), "padded reads leave the A/W planes");
+    static_assert((NX - 1) * LDU + 2 - (NX / 2 - 1) + STEPS_PAD + 1 + LDU <= (NX + 2) * LDU, "padded reads leave the (u, v) plane");
 #pragma unroll 6
     for (int t = 0; t < STEPS_PAD; t++) {
         // fetch two columns ahead
         const double2 an2 = lds128_f64(aA + (uint32_t)(t + 1) * 16u), wn2 = lds128_f64(aW + (uint32_t)(t + 1) * 16u);
-        const double v0n2 = lds64_f64(aV + (uint32_t)(t + 1) * 8u), v1n2 = lds64_f64(aV + LD * 8u + (uint32_t)(t + 1) * 8u);
+        const double v0n2 = lds64_f64(aV + (uint32_t)(t + 1) * 16u), v1n2 = lds64_f64(aV + LDU * 16u + (uint32_t)(t + 1) * 16u);
         const double wv = __shfl_up_sync(0xffffffffu, last_new, 1);
         const int act_ = (unsigned)(c0 + t) < (unsigned)NY;
         const double s0n = fma(hk, v0n, dky), s1n = fma(hk, v1n, dky);
@@ -565,9 +570,18 @@ constexpr int mac_ldp(int ld, int ti) { int l = ld; while ((ti * l) % 16 != 2) l
 template <typename R, int NX, int NY, int TI, int TJ, int T, bool DBG>
 __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
 {
-    constexpr int LD = NY + 2, N = (NX + 2) * LD;       // field planes
-    constexpr int LDP = mac_ldp(LD, TI);                // exchange planes: conflict-free stride
-    constexpr int NP = (NX + 2) * LDP;
+    typedef typename vec2_of<R>::type R2;
+    constexpr int LD = NY + 2, N = (NX + 2) * LD;       // field planes in global memory
+    constexpr int LDP = mac_ldp(LD, TI);                // exchange planes: conflict-free stride (8-byte elements)
+    constexpr int NP = ((NX + 1) * LDP + 3) / 4 * 4;    // rows 0 .. NX (no ghost row NX+1: wall tiles read their own edge)
+    // u and v live INTERLEAVED in one plane of (u, v) pairs: the tile origins of a quarter-warp fall into 8 distinct
+    // 16-byte bank groups iff 2 LDU = 2 mod 8 (LDU = 53), one LDS.128 fetches both components, and every access is
+    // conflict free — two separate planes of stride NY+2 = 52 cannot be (the banks 0, 5, 8, 13 are oversubscribed for
+    // 2x5 tiles whatever the thread mapping; a stride of 57 for each does not fit twice per SM).  T uses the stride
+    // of the exchange planes.  Measured: shared-memory bank conflicts were 25 % of all wavefronts before.
+    constexpr int LDU = ((LD + 2) / 4) * 4 + 1, NU = (NX + 2) * LDU;      // in (u, v) pairs
+    constexpr int LDT = LDP, NT = (NX + 2) * LDT;
+    static_assert(TI != 2 || (2 * LDU) % 8 == 2, "u/v plane stride");
     constexpr int TILES_J = NY / TJ, TILES = (NX / TI) * TILES_J, NW = T / 32;
     static_assert(NX % TI == 0 && NY % TJ == 0 && TILES <= T, "tiles must cover the grid exactly");
     static_assert(NX <= 64, "transport wavefront: two rows per lane");
@@ -576,20 +590,22 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
     __shared__ R s_exact[NW];                         // fp64 warp partials, only when the fp32 total is too close to tol
     __shared__ R s_seg[32];
     __shared__ R s_act[32];
-    __shared__ __align__(8) uint64_t s_mbar;
-    static_assert((N * sizeof(R)) % 16 == 0 && (NP * sizeof(R)) % 16 == 0, "bulk copies need 16-byte multiples");
+    static_assert((NP * sizeof(R)) % 16 == 0, "planes must stay 16-byte aligned");
     const int tid = threadIdx.x, b = blockIdx.x;
     const bool resetting = a.mode == 1;
     if (resetting && a.mask && !a.mask[b]) return;
 
-    R *PA = reinterpret_cast<R *>(smem_raw), *PB = PA + NP, *U = PB + NP, *V = U + N, *S = V + N;
+    R *PA = reinterpret_cast<R *>(smem_raw), *PB = PA + NP;
+    R2 *UV = reinterpret_cast<R2 *>(PB + NP);
+    R *S = reinterpret_cast<R *>(UV + NU);
     const size_t row = (size_t)b * N;
     R *gu = a.u + row, *gv = a.v + row, *gp = a.p + row, *gs = a.s + row;
 
     const bool has_tile = tid < TILES;
     const int ti = tid / TILES_J, tj = tid - ti * TILES_J;
     const int i0 = 1 + ti * TI, j0 = 1 + tj * TJ;
-    const int o = i0 * LD + j0, op = i0 * LDP + j0;     // tile origin in field / exchange planes
+    const int o = i0 * LD + j0, op = i0 * LDP + j0;     // tile origin in global field / exchange planes
+    const int ou = i0 * LDU + j0, ot = i0 * LDT + j0;   // ... in the (u, v) plane and in the T plane
     const int opx = has_tile ? op : LDP + 1;             // threads without a tile shadow tile 0 in the sweeps (weight 0)
     const bool top = has_tile && i0 == 1, bot = has_tile && i0 + TI - 1 == NX;
     const bool lef = has_tile && j0 == 1, rig = has_tile && j0 + TJ - 1 == NY;
@@ -626,16 +642,18 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
         return;
     }
     for (int e = tid; e < 2 * NP; e += T) PA[e] = R(0);   // masked wavefront steps read padding slots: keep them finite
-    // state planes global -> shared: three bulk copies issued by one thread (TMA engine, no registers)
-    if (tid == 0) { mbar_init(&s_mbar, 1); fence_async_smem(); }
-    __syncthreads();
-    if (tid == 0) {
-        mbar_expect_tx(&s_mbar, 3u * (uint32_t)(N * sizeof(R)));
-        bulk_g2s(U, gu, (uint32_t)(N * sizeof(R)), &s_mbar);
-        bulk_g2s(V, gv, (uint32_t)(N * sizeof(R)), &s_mbar);
-        bulk_g2s(S, gs, (uint32_t)(N * sizeof(R)), &s_mbar);
+    // state planes global -> shared, into the padded / interleaved layouts (once per launch)
+    for (int e = tid; e < N; e += T) {
+        const int i = e / LD, j = e - i * LD;
+        R2 w; w.x = gu[e]; w.y = gv[e];
+        UV[i * LDU + j] = w;
+        S[i * LDT + j] = gs[e];
     }
-    mbar_wait(&s_mbar, 0);
+    for (int e = tid; e < NX + 2; e += T) {            // padding columns: read by masked wavefront steps, keep them finite
+        for (int j = LD; j < LDU; j++) { R2 z; z.x = R(0); z.y = R(0); UV[e * LDU + j] = z; }
+        for (int j = LD; j < LDT; j++) S[e * LDT + j] = R(0);
+    }
+    __syncthreads();
     // Ghost cells of p only ever accumulate the same increments as their wall-adjacent cells (phi
     // ghosts are copies) and never feed back: they are brought up to date once, at the end of the
     // launch, from the launch-initial values of the adjacent cells saved in the `us` workspace plane.
@@ -668,26 +686,29 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
 
         for (int it = 0; it < a.ndt_act; it++) {
             // ---- boundary conditions, rayleigh.py:180-202 ------------------------------------------
+#define UU(i, j) UV[(i) * LDU + (j)].x
+#define VV(i, j) UV[(i) * LDU + (j)].y
+#define SS(i, j) S[(i) * LDT + (j)]
             for (int k = tid; k < 2 * (NX + 2) + 2 * (NY + 2); k += T) {
                 if (k < NY + 2) {
                     int j = k;
-                    if (j >= 1 && j <= NY) { U[1 * LD + j] = R(0); S[0 * LD + j] = S[1 * LD + j]; }
-                    if (j >= 2 && j <= NY) V[0 * LD + j] = -V[1 * LD + j];
+                    if (j >= 1 && j <= NY) { UU(1, j) = R(0); SS(0, j) = SS(1, j); }
+                    if (j >= 2 && j <= NY) VV(0, j) = -VV(1, j);
                 } else if (k < 2 * (NY + 2)) {
                     int j = k - (NY + 2);
-                    if (j >= 1 && j <= NY) { U[(NX + 1) * LD + j] = R(0); S[(NX + 1) * LD + j] = S[NX * LD + j]; }
-                    if (j >= 2 && j <= NY) V[(NX + 1) * LD + j] = -V[NX * LD + j];
+                    if (j >= 1 && j <= NY) { UU(NX + 1, j) = R(0); SS(NX + 1, j) = SS(NX, j); }
+                    if (j >= 2 && j <= NY) VV(NX + 1, j) = -VV(NX, j);
                 } else if (k < 2 * (NY + 2) + (NX + 2)) {
                     int i = k - 2 * (NY + 2);
-                    if (i >= 1 && i <= NX + 1) U[i * LD + NY + 1] = (i == 1 || i == NX + 1) ? -R(0) : -U[i * LD + NY];
-                    if (i >= 1 && i <= NX) { V[i * LD + NY + 1] = R(0); S[i * LD + NY + 1] = R(2) * a.Tc - S[i * LD + NY]; }
+                    if (i >= 1 && i <= NX + 1) UU(i, NY + 1) = (i == 1 || i == NX + 1) ? -R(0) : -UU(i, NY);
+                    if (i >= 1 && i <= NX) { VV(i, NY + 1) = R(0); SS(i, NY + 1) = R(2) * a.Tc - SS(i, NY); }
                 } else {
                     int i = k - 2 * (NY + 2) - (NX + 2);
-                    if (i >= 1 && i <= NX + 1) U[i * LD + 0] = (i == 1 || i == NX + 1) ? -R(0) : -U[i * LD + 1];
+                    if (i >= 1 && i <= NX + 1) UU(i, 0) = (i == 1 || i == NX + 1) ? -R(0) : -UU(i, 1);
                     if (i >= 1 && i <= NX) {
-                        V[i * LD + 1] = R(0);
+                        VV(i, 1) = R(0);
                         int sg = (i - 1) / a.nx_sgts;
-                        if (sg < a.n_sgts) S[i * LD + 0] = R(2) * s_seg[sg] - S[i * LD + 1];
+                        if (sg < a.n_sgts) SS(i, 0) = R(2) * s_seg[sg] - SS(i, 1);
                     }
                 }
             }
@@ -697,33 +718,37 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
             // ---- predictor into registers, rayleigh.py:371-407 -----------------------------------------
             R us[TI][TJ], vs[TI][TJ];
             if (has_tile) {
-                const R *u = U + o, *v = V + o, *sc = S + o, *p = gp + o;
+                const R2 *uv = UV + ou;
+                const R *sc = S + ot, *p = gp + o;
+                // (u, v) pairs of the tile and its one-cell ring are fetched as 16-byte words where they are used (equal
+                // addresses are merged by the compiler)
                 TILE_LOOP {
-                    const int e = r * LD + k;
-                    const R uc = u[e], vc = v[e], pc = p[e];
+                    const R2 *q = uv + r * LDU + k;
+                    const R2 c = q[0], E = q[LDU], W = q[-LDU], Nn = q[1], Ss = q[-1];
+                    const R uc = c.x, vc = c.y, pc = p[r * LD + k];
                     us[r][k] = uc; vs[r][k] = vc;
                     if (r > 0 || !top) {               // i >= 2
-                        R uE = R(0.5) * (u[e + LD] + uc), uW = R(0.5) * (uc + u[e - LD]);
-                        R uN = R(0.5) * (u[e + 1] + uc), uS = R(0.5) * (uc + u[e - 1]);
-                        R vN = R(0.5) * (v[e + 1] + v[e - LD + 1]), vS = R(0.5) * (vc + v[e - LD]);
+                        R uE = R(0.5) * (E.x + uc), uW = R(0.5) * (uc + W.x);
+                        R uN = R(0.5) * (Nn.x + uc), uS = R(0.5) * (uc + Ss.x);
+                        R vN = R(0.5) * (Nn.y + q[-LDU + 1].y), vS = R(0.5) * (vc + W.y);
                         R conv = (uE * uE - uW * uW) * inv_dx + (uN * vN - uS * vS) * inv_dy;
-                        R diff = ((u[e + LD] - R(2) * uc + u[e - LD]) * a.inv_dx2 + (u[e + 1] - R(2) * uc + u[e - 1]) * a.inv_dy2) * a.dcoef;
-                        R pres = (pc - p[e - LD]) * inv_dx;
+                        R diff = ((E.x - R(2) * uc + W.x) * a.inv_dx2 + (Nn.x - R(2) * uc + Ss.x) * a.inv_dy2) * a.dcoef;
+                        R pres = (pc - p[r * LD + k - LD]) * inv_dx;
                         us[r][k] = uc + dt * (diff - conv - pres);
                     }
                     if (k > 0 || !lef) {               // j >= 2
-                        R vE = R(0.5) * (v[e + LD] + vc), vW = R(0.5) * (vc + v[e - LD]);
-                        R uE = R(0.5) * (u[e + LD] + u[e + LD - 1]), uW = R(0.5) * (uc + u[e - 1]);
-                        R vN = R(0.5) * (v[e + 1] + vc), vS = R(0.5) * (vc + v[e - 1]);
+                        R vE = R(0.5) * (E.y + vc), vW = R(0.5) * (vc + W.y);
+                        R uE = R(0.5) * (E.x + q[LDU - 1].x), uW = R(0.5) * (uc + Ss.x);
+                        R vN = R(0.5) * (Nn.y + vc), vS = R(0.5) * (vc + Ss.y);
                         R conv = (uE * vE - uW * vW) * inv_dx + (vN * vN - vS * vS) * inv_dy;
-                        R diff = ((v[e + LD] - R(2) * vc + v[e - LD]) * a.inv_dx2 + (v[e + 1] - R(2) * vc + v[e - 1]) * a.inv_dy2) * a.dcoef;
-                        R pres = (pc - p[e - 1]) * inv_dy;
-                        vs[r][k] = vc + dt * (diff - conv - pres + sc[e]);
+                        R diff = ((E.y - R(2) * vc + W.y) * a.inv_dx2 + (Nn.y - R(2) * vc + Ss.y) * a.inv_dy2) * a.dcoef;
+                        R pres = (pc - p[r * LD + k - 1]) * inv_dy;
+                        vs[r][k] = vc + dt * (diff - conv - pres + sc[r * LDT + k]);
                     }
                 }
             }
             __syncthreads();                       // every read of the old u, v is done
-            if (has_tile) { TILE_LOOP { U[o + r * LD + k] = us[r][k]; V[o + r * LD + k] = vs[r][k]; } }
+            if (has_tile) { TILE_LOOP { R2 w; w.x = us[r][k]; w.y = vs[r][k]; UV[ou + r * LDU + k] = w; } }
             __syncthreads();                       // U, V now hold the starred fields (walls: 0)
             PHASE(1);
 
@@ -834,8 +859,8 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
                     for (int k = 0; k < TJ; k++) {
                         R cv = R(0);
                         if (has_tile) {
-                            const R ue = (r < TI - 1) ? us[r + 1][k] : U[o + (r + 1) * LD + k];
-                            const R vn = (k < TJ - 1) ? vs[r][k + 1] : V[o + r * LD + k + 1];
+                            const R ue = (r < TI - 1) ? us[r + 1][k] : UV[ou + (r + 1) * LDU + k].x;
+                            const R vn = (k < TJ - 1) ? vs[r][k + 1] : UV[ou + r * LDU + k + 1].y;
                             cv = -(((ue - us[r][k]) * inv_dx + (vn - vs[r][k]) * inv_dy) * a.cscale) * a.inv_den;
                         }
                         cn[r][k] = cv; phi[r][k] = cv;
@@ -889,12 +914,14 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
 
             // ---- p += phi (rayleigh.py:219; ghost cells: see the end of the launch) and in-place corrector (:461-464)
             if (has_tile) {
-                R *p = gp + o, *u = U + o, *v = V + o;
+                R *p = gp + o;
+                R2 *uv = UV + ou;
                 TILE_LOOP {
-                    const int e = r * LD + k;
-                    p[e] += phi[r][k];
-                    if (r > 0 || !top) { const R pw = (r > 0) ? phi[r - 1][k] : pf[-LDP + k]; u[e] = u[e] - dt * (phi[r][k] - pw) * inv_dx; }
-                    if (k > 0 || !lef) { const R ps = (k > 0) ? phi[r][k - 1] : pf[r * LDP - 1]; v[e] = v[e] - dt * (phi[r][k] - ps) * inv_dy; }
+                    p[r * LD + k] += phi[r][k];
+                    R2 w = uv[r * LDU + k];
+                    if (r > 0 || !top) { const R pw = (r > 0) ? phi[r - 1][k] : pf[-LDP + k]; w.x = w.x - dt * (phi[r][k] - pw) * inv_dx; }
+                    if (k > 0 || !lef) { const R ps = (k > 0) ? phi[r][k - 1] : pf[r * LDP - 1]; w.y = w.y - dt * (phi[r][k] - ps) * inv_dy; }
+                    uv[r * LDU + k] = w;
                 }
             }
             __syncthreads();
@@ -911,16 +938,18 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
                 static_assert(2 * (NX / 2) * RS <= NP, "wavefront planes must fit the exchange planes");
                 const R kx = a.tcoef * a.inv_dx2, ky = a.tcoef * a.inv_dy2;
                 if (has_tile) {
-                    const R *u = U + o, *v = V + o, *sc = S + o;
+                    const R2 *uv = UV + ou;
+                    const R *sc = S + ot;
                     TILE_LOOP {
-                        const int e = r * LD + k;
-                        const R uE = u[e + LD], uW = u[e], vN = v[e + 1], vS = v[e];
-                        const R s0 = sc[e], sE = sc[e + LD], sN = sc[e + 1];
+                        const int e = r * LDT + k;
+                        const R2 c = uv[r * LDU + k];
+                        const R uE = uv[(r + 1) * LDU + k].x, uW = c.x, vN = uv[r * LDU + k + 1].y, vS = c.y;
+                        const R s0 = sc[e], sE = sc[e + LDT], sN = sc[e + 1];
                         R diff0 = ((sE - R(2) * s0) * a.inv_dx2 + (sN - R(2) * s0) * a.inv_dy2) * a.tcoef;
                         R conv0 = (uE * (R(0.5) * (sE + s0)) - uW * (R(0.5) * s0)) * inv_dx + (vN * (R(0.5) * (sN + s0)) - vS * (R(0.5) * s0)) * inv_dy;
                         R A = s0 + dt * (diff0 - conv0);
                         R BW = dt * (kx + R(0.5) * uW * inv_dx);
-                        if (r == 0 && top) { A = fma(BW, sc[e - LD], A); BW = R(0); }
+                        if (r == 0 && top) { A = fma(BW, sc[e - LDT], A); BW = R(0); }
                         const int gi = TI * ti + r, idx = ((gi >> 1) * RS + j0 + k) * 2 + (gi & 1);   // [row pair][column][row in pair]
                         PA[idx] = A;
                         PB[idx] = BW;
@@ -931,8 +960,8 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
                 if (tid < 32) {
                     const R hk = R(0.5) * dt * inv_dy, dky = dt * ky;
                     if constexpr (std::is_same<R, double>::value) {
-                        transport_wavefront_f64<NX, NY, LD>((uint32_t)__cvta_generic_to_shared(PA), (uint32_t)__cvta_generic_to_shared(PB),
-                                                            (uint32_t)__cvta_generic_to_shared(V), (uint32_t)__cvta_generic_to_shared(S), hk, dky, tid);
+                        transport_wavefront_f64<NX, NY, LDU, LDT>((uint32_t)__cvta_generic_to_shared(PA), (uint32_t)__cvta_generic_to_shared(PB),
+                                                                  (uint32_t)__cvta_generic_to_shared(UV), (uint32_t)__cvta_generic_to_shared(S), hk, dky, tid);
                     } else {
                         // Lane l owns rows 2l+1, 2l+2 and does column j = t - l + 1 at step t.  The loop is
                         // uniform: inactive steps (j outside 1..NY) compute on harmless in-bounds garbage and
@@ -942,16 +971,17 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
                         const int lane = tid;
                         const bool on = lane < LANES;
                         const int l = on ? lane : 0;
-                        const R *Vr0 = V + (2 * l + 1) * LD, *Vr1 = Vr0 + LD;
-                        R *Sr0 = S + (2 * l + 1) * LD, *Sr1 = Sr0 + LD;
+                        const R2 *Vr0 = UV + (2 * l + 1) * LDU, *Vr1 = Vr0 + LDU;
+                        R *Sr0 = S + (2 * l + 1) * LDT, *Sr1 = Sr0 + LDT;
                         const R *AAr = PA + (size_t)l * RS * 2, *WWr = PB + (size_t)l * RS * 2;
                         // column 1: partial sums with the south ghost (column 0, untouched by transport)
-                        R p0 = fma(fma(hk, Vr0[1], dky), Sr0[0], AAr[2]), p1 = fma(fma(hk, Vr1[1], dky), Sr1[0], AAr[3]);
+                        R p0 = fma(fma(hk, Vr0[1].y, dky), Sr0[0], AAr[2]), p1 = fma(fma(hk, Vr1[1].y, dky), Sr1[0], AAr[3]);
                         R w0 = WWr[2], w1 = WWr[3];
                         R last_new = R(0);
                         // pointers biased by -lane: element [t] is column t - lane + 2 (prefetch) / t - lane + 1 (store)
                         // (lanes beyond the last row pair mimic lane 0 with the predicate off)
-                        const R *An = AAr + 2 * (2 - l), *Wn = WWr + 2 * (2 - l), *V0n = Vr0 + (2 - l), *V1n = Vr1 + (2 - l);
+                        const R *An = AAr + 2 * (2 - l), *Wn = WWr + 2 * (2 - l);
+                        const R2 *V0n = Vr0 + (2 - l), *V1n = Vr1 + (2 - l);
                         R *S0o = Sr0 + (1 - l), *S1o = Sr1 + (1 - l);
                         const int c0 = on ? -lane : -(1 << 20);
     #pragma unroll 2
@@ -959,7 +989,7 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
                             const R wv = __shfl_up_sync(0xffffffffu, last_new, 1);
                             const bool act_ = (unsigned)(c0 + t) < (unsigned)NY;
                             const R a0n = An[2 * t], a1n = An[2 * t + 1], w0n = Wn[2 * t], w1n = Wn[2 * t + 1];
-                            const R s0n = fma(hk, V0n[t], dky), s1n = fma(hk, V1n[t], dky);
+                            const R s0n = fma(hk, V0n[t].y, dky), s1n = fma(hk, V1n[t].y, dky);
                             const R n0 = fma(w0, wv, p0);
                             const R n1 = fma(w1, n0, p1);
                             last_new = n1;
@@ -989,18 +1019,22 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
                     int f = rem / (a.nx_obs_pts * a.ny_obs_pts), q = rem - f * (a.nx_obs_pts * a.ny_obs_pts);
                     int pi = q / a.ny_obs_pts, pj = q - pi * a.ny_obs_pts;
                     int x = a.nx_obs / 2 + pi * a.nx_obs, y = a.ny_obs / 2 + pj * a.ny_obs;
-                    val = (f == 0) ? S[x * LD + y] : (f == 1 ? U[x * LD + y] : V[x * LD + y]);
+                    val = (f == 0) ? SS(x, y) : (f == 1 ? UU(x, y) : VV(x, y));
                 }
                 out[e] = val;
             }
             __syncthreads();
             for (int e = tid; e < a.n_obs; e += T) hist[e] = out[e];
             bool nonfinite = false;
-            for (int e = tid; e < N; e += T) nonfinite |= !finite_(S[e]) | !finite_(U[e]) | !finite_(V[e]);
+            for (int e = tid; e < N; e += T) {
+                const int i = e / LD, j = e - i * LD;
+                const R2 w = UV[i * LDU + j];
+                nonfinite |= !finite_(SS(i, j)) | !finite_(w.x) | !finite_(w.y);
+            }
             if (__syncthreads_or(nonfinite ? 1 : 0)) status |= BEACON_STATUS_NONFINITE;
             if (tid == 0) {
                 R nu = R(0);
-                for (int i = 1; i <= NX; i++) nu -= (S[i * LD + 1] - a.Th) / (R(0.5) * a.dy);
+                for (int i = 1; i <= NX; i++) nu -= (SS(i, 1) - a.Th) / (R(0.5) * a.dy);
                 nu /= R(NX);
                 a.rwd[orow] = -nu;
                 bool horizon = stp == a.n_act - 1;
@@ -1011,13 +1045,11 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
         }
     }   // actions
 
-    fence_async_smem();                                // my generic writes to U, V, S -> visible to the bulk engine
     __syncthreads();
-    if (tid == 0) {                                    // state planes shared -> global
-        bulk_s2g(gu, U, (uint32_t)(N * sizeof(R)));
-        bulk_s2g(gv, V, (uint32_t)(N * sizeof(R)));
-        bulk_s2g(gs, S, (uint32_t)(N * sizeof(R)));
-        bulk_commit_wait_all();
+    for (int e = tid; e < N; e += T) {                 // state planes shared -> global
+        const int i = e / LD, j = e - i * LD;
+        const R2 w = UV[i * LDU + j];
+        gu[e] = w.x; gv[e] = w.y; gs[e] = SS(i, j);
     }
     if (has_tile && (top || bot || lef || rig)) {      // ghost cells of p += this launch's increments of the adjacent cell
         R *p = gp + o;
@@ -1043,6 +1075,9 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
     if (DBG && dbg) { for (int n = 0; n < (DBG ? 8 : 1); n++) a.dbg[n] += (unsigned long long)tph[n]; }
 #undef PHASE
 #undef TILE_LOOP
+#undef UU
+#undef VV
+#undef SS
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1056,9 +1091,6 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
 // wipes out, steps after its last column are masked by the store predicate.  New values
 // overwrite A in place.  Per step: 3 x 16-byte loads, 2 shuffles, 4 FMAs, one predicated store.
 // ---------------------------------------------------------------------------------------
-template <typename R> struct vec2_of;
-template <> struct vec2_of<double> { typedef double2 type; };
-template <> struct vec2_of<float> { typedef float2 type; };
 
 template <typename R, int NY>
 __device__ __noinline__ void transport_wavefront3(uint32_t offA, uint32_t offW, uint32_t offS, int lanes, int lane)
@@ -1150,7 +1182,7 @@ __global__ void __launch_bounds__(T, MINB) mac_big_kernel(const MacArgs<R> a)
     // phi(i, NY+1) = 0 (mixing.py:451) is a constant.  Threads without a tile shadow tile 0.
     const int tix = has_tile ? ti : 0, tjx = has_tile ? tj : 0;
     const int o_n = tix == 0 ? 0 : -LDP, o_s = tix == NX / TI - 1 ? (TI - 1) * LDP : TI * LDP;
-    const int o_w = tjx == 0 ? 0 : -1, o_e = tjx == TILES_J - 1 ? TJ - 1 : TJ;
+    const bool lefx = tjx == 0, rigx = tjx == TILES_J - 1;
     const bool dir_e = rig && !ray;
 #define TILE_LOOP                                      \
     _Pragma("unroll") for (int r = 0; r < TI; r++)     \
@@ -1340,9 +1372,10 @@ __global__ void __launch_bounds__(T, MINB) mac_big_kernel(const MacArgs<R> a)
             auto sweep = [&](R (&ph)[TI][TJ], const R *pi, float &wsum) -> R {
                 // in place, column by column; halo values are fetched where they are used (register budget)
                 R rs[TI], po_[TI], cl = R(0), cr = R(0);
-                const R *pn = pi + o_n, *ps = pi + o_s, *pw = pi + o_w, *pe = pi + o_e;
+                const R *pn = pi + o_n, *ps = pi + o_s;
+                // west / east halo at uniform offsets (conflict free); wall tiles use their own edge column (registers)
 #pragma unroll
-                for (int r = 0; r < TI; r++) { rs[r] = R(0); po_[r] = pw[r * LDP]; }
+                for (int r = 0; r < TI; r++) { rs[r] = R(0); const R hw = pi[r * LDP - 1]; po_[r] = lefx ? ph[r][0] : hw; }
 #pragma unroll
                 for (int k = 0; k < TJ; k++) {
                     if (k < 5) wsum += __shfl_xor_sync(0xffffffffu, wsum, 16 >> k);
@@ -1353,7 +1386,10 @@ __global__ void __launch_bounds__(T, MINB) mac_big_kernel(const MacArgs<R> a)
 #pragma unroll
                     for (int r = 0; r < TI; r++) {
                         const R xm = (r > 0) ? old[r - 1] : hnk, xp = (r < TI - 1) ? old[r + 1] : hsk;
-                        const R ym = po_[r], yp = (k < TJ - 1) ? ph[r][k + 1] : (dir_e ? R(0) : pe[r * LDP]);
+                        R yp;
+                        if (k < TJ - 1) yp = ph[r][k + 1];
+                        else { const R he = pi[r * LDP + TJ]; yp = dir_e ? R(0) : (rigx ? old[r] : he); }
+                        const R ym = po_[r];
                         const R nv = fma(xp + xm, a.pk1, fma(yp + ym, a.pk2, cn[r][k]));
                         const R d = nv - old[r];
                         rs[r] = fma(d, d, rs[r]);
@@ -1628,7 +1664,7 @@ public:
         const size_t plane = (size_t)n * sizeof(R);
         int TI, TJ;
         reg_variant = false;
-        if (ray && nx == 50 && ny == 50 && sizeof(R) * (2 * 52 * 57 + 3 * 52 * 52) <= 113 * 1024 && p.n_sgts <= 32 && !getenv("BEACON_MAC_V1")) {
+        if (ray && nx == 50 && ny == 50 && p.n_sgts <= 32 && !getenv("BEACON_MAC_V1")) {
             // five planes fit twice per SM: register-resident phi tiles, 2 CTAs/SM
             const char *tile = getenv("BEACON_MAC_TILE");              // tuning: "5x5" = 100 threads with 25 cells each
             if (tile && !strcmp(tile, "5x5")) {
@@ -1639,7 +1675,7 @@ public:
                 else kernel = mac_reg_kernel<R, 50, 50, 2, 5, 256, false>;
                 T = 256; TI = 2; TJ = 5; dbg_variant = true;
             }
-            smem = sizeof(R) * (2 * 52 * mac_ldp(52, TI) + 3 * 52 * 52); reg_variant = true;
+            smem = sizeof(R) * (2 * (size_t)((51 * mac_ldp(52, TI) + 3) / 4 * 4) + 2 * 52 * 53 + 52 * mac_ldp(52, TI)); reg_variant = true;
         } else if (nx == 100 && ny == 100 && !getenv("BEACON_MAC_V1")) {
             // register-resident Poisson, fields in L2: one CTA of 500 tile threads per SM
             if (getenv("BEACON_MAC_DEBUG")) kernel = mac_big_kernel<R, 100, 100, 4, 5, 512, 1, true>;
