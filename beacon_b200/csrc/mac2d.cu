@@ -684,67 +684,161 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
         __syncthreads();
         long long it_total = 0;
 
-        for (int it = 0; it < a.ndt_act; it++) {
-            // ---- boundary conditions, rayleigh.py:180-202 ------------------------------------------
 #define UU(i, j) UV[(i) * LDU + (j)].x
 #define VV(i, j) UV[(i) * LDU + (j)].y
 #define SS(i, j) S[(i) * LDT + (j)]
-            for (int k = tid; k < 2 * (NX + 2) + 2 * (NY + 2); k += T) {
+        // ---- boundary conditions, rayleigh.py:180-202, split by field: the velocity ghosts do not depend on T, the
+        // T ghosts need the transported T.  Executed by the threads t0, t0 + nt, ... of the caller's group.
+        auto bc_uv = [&](const int t0, const int nt, const bool walls) {
+            for (int k = t0; k < 2 * (NX + 2) + 2 * (NY + 2); k += nt) {
                 if (k < NY + 2) {
                     int j = k;
-                    if (j >= 1 && j <= NY) { UU(1, j) = R(0); SS(0, j) = SS(1, j); }
+                    if (walls && j >= 1 && j <= NY) UU(1, j) = R(0);
                     if (j >= 2 && j <= NY) VV(0, j) = -VV(1, j);
                 } else if (k < 2 * (NY + 2)) {
                     int j = k - (NY + 2);
-                    if (j >= 1 && j <= NY) { UU(NX + 1, j) = R(0); SS(NX + 1, j) = SS(NX, j); }
+                    if (walls && j >= 1 && j <= NY) UU(NX + 1, j) = R(0);
                     if (j >= 2 && j <= NY) VV(NX + 1, j) = -VV(NX, j);
                 } else if (k < 2 * (NY + 2) + (NX + 2)) {
                     int i = k - 2 * (NY + 2);
                     if (i >= 1 && i <= NX + 1) UU(i, NY + 1) = (i == 1 || i == NX + 1) ? -R(0) : -UU(i, NY);
-                    if (i >= 1 && i <= NX) { VV(i, NY + 1) = R(0); SS(i, NY + 1) = R(2) * a.Tc - SS(i, NY); }
+                    if (walls && i >= 1 && i <= NX) VV(i, NY + 1) = R(0);
                 } else {
                     int i = k - 2 * (NY + 2) - (NX + 2);
                     if (i >= 1 && i <= NX + 1) UU(i, 0) = (i == 1 || i == NX + 1) ? -R(0) : -UU(i, 1);
+                    if (walls && i >= 1 && i <= NX) VV(i, 1) = R(0);
+                }
+            }
+        };
+        auto bc_s = [&](const int t0, const int nt) {
+            for (int k = t0; k < 2 * (NX + 2) + 2 * (NY + 2); k += nt) {
+                if (k < NY + 2) {
+                    int j = k;
+                    if (j >= 1 && j <= NY) SS(0, j) = SS(1, j);
+                } else if (k < 2 * (NY + 2)) {
+                    int j = k - (NY + 2);
+                    if (j >= 1 && j <= NY) SS(NX + 1, j) = SS(NX, j);
+                } else if (k < 2 * (NY + 2) + (NX + 2)) {
+                    int i = k - 2 * (NY + 2);
+                    if (i >= 1 && i <= NX) SS(i, NY + 1) = R(2) * a.Tc - SS(i, NY);
+                } else {
+                    int i = k - 2 * (NY + 2) - (NX + 2);
                     if (i >= 1 && i <= NX) {
-                        VV(i, 1) = R(0);
                         int sg = (i - 1) / a.nx_sgts;
                         if (sg < a.n_sgts) SS(i, 0) = R(2) * s_seg[sg] - SS(i, 1);
                     }
                 }
             }
-            __syncthreads();
+        };
+        // ---- predictor into registers, rayleigh.py:371-407: us = u*, vx = the right-hand side of v* WITHOUT the
+        // buoyancy term (v* = v + dt (vx + T) is formed later with the transported T: the same operations in the same
+        // order as the reference's expression)
+        R us[TI][TJ], vs[TI][TJ];
+        auto predictor = [&]() {
+            const R2 *uv = UV + ou;
+            const R *p = gp + o;
+            // (u, v) pairs of the tile and its one-cell ring are fetched as 16-byte words where they are used (equal
+            // addresses are merged by the compiler)
+            TILE_LOOP {
+                const R2 *q = uv + r * LDU + k;
+                const R2 c = q[0], E = q[LDU], W = q[-LDU], Nn = q[1], Ss = q[-1];
+                const R uc = c.x, vc = c.y, pc = p[r * LD + k];
+                us[r][k] = uc; vs[r][k] = R(0);
+                if (r > 0 || !top) {               // i >= 2
+                    R uE = R(0.5) * (E.x + uc), uW = R(0.5) * (uc + W.x);
+                    R uN = R(0.5) * (Nn.x + uc), uS = R(0.5) * (uc + Ss.x);
+                    R vN = R(0.5) * (Nn.y + q[-LDU + 1].y), vS = R(0.5) * (vc + W.y);
+                    R conv = (uE * uE - uW * uW) * inv_dx + (uN * vN - uS * vS) * inv_dy;
+                    R diff = ((E.x - R(2) * uc + W.x) * a.inv_dx2 + (Nn.x - R(2) * uc + Ss.x) * a.inv_dy2) * a.dcoef;
+                    R pres = (pc - p[r * LD + k - LD]) * inv_dx;
+                    us[r][k] = uc + dt * (diff - conv - pres);
+                }
+                if (k > 0 || !lef) {               // j >= 2
+                    R vE = R(0.5) * (E.y + vc), vW = R(0.5) * (vc + W.y);
+                    R uE = R(0.5) * (E.x + q[LDU - 1].x), uW = R(0.5) * (uc + Ss.x);
+                    R vN = R(0.5) * (Nn.y + vc), vS = R(0.5) * (vc + Ss.y);
+                    R conv = (uE * vE - uW * vW) * inv_dx + (vN * vN - vS * vS) * inv_dy;
+                    R diff = ((E.y - R(2) * vc + W.y) * a.inv_dx2 + (Nn.y - R(2) * vc + Ss.y) * a.inv_dy2) * a.dcoef;
+                    R pres = (pc - p[r * LD + k - 1]) * inv_dy;
+                    vs[r][k] = diff - conv - pres;
+                }
+            }
+        };
+        const R kx = a.tcoef * a.inv_dx2, ky = a.tcoef * a.inv_dy2;
+        constexpr int RS = wavefront_row_stride(NY);       // columns 0..NY per row pair (0 unused), padded
+        static_assert(NX % 2 == 0 && NX / 2 <= 32, "wavefront layout: one lane per row pair");
+        static_assert(2 * (NX / 2) * RS <= NP, "wavefront planes must fit the exchange planes");
+        auto wavefront = [&]() {
+            const R hk = R(0.5) * dt * inv_dy, dky = dt * ky;
+            if constexpr (std::is_same<R, double>::value) {
+                transport_wavefront_f64<NX, NY, LDU, LDT>((uint32_t)__cvta_generic_to_shared(PA), (uint32_t)__cvta_generic_to_shared(PB),
+                                                          (uint32_t)__cvta_generic_to_shared(UV), (uint32_t)__cvta_generic_to_shared(S), hk, dky, tid);
+            } else {
+                // Lane l owns rows 2l+1, 2l+2 and does column j = t - l + 1 at step t.  The loop is
+                // uniform: inactive steps (j outside 1..NY) compute on harmless in-bounds garbage and
+                // are masked by ONE predicate (stores, partial sums); per step the dependent chain is
+                // SHFL + 2 DFMA, the coefficients of column j+1 are fetched while it waits.
+                constexpr int LANES = NX / 2, STEPS = NY + LANES - 1;
+                const int lane = tid;
+                const bool on = lane < LANES;
+                const int l = on ? lane : 0;
+                const R2 *Vr0 = UV + (2 * l + 1) * LDU, *Vr1 = Vr0 + LDU;
+                R *Sr0 = S + (2 * l + 1) * LDT, *Sr1 = Sr0 + LDT;
+                const R *AAr = PA + (size_t)l * RS * 2, *WWr = PB + (size_t)l * RS * 2;
+                // column 1: partial sums with the south ghost (column 0, untouched by transport)
+                R p0 = fma(fma(hk, Vr0[1].y, dky), Sr0[0], AAr[2]), p1 = fma(fma(hk, Vr1[1].y, dky), Sr1[0], AAr[3]);
+                R w0 = WWr[2], w1 = WWr[3];
+                R last_new = R(0);
+                // pointers biased by -lane: element [t] is column t - lane + 2 (prefetch) / t - lane + 1 (store)
+                // (lanes beyond the last row pair mimic lane 0 with the predicate off)
+                const R *An = AAr + 2 * (2 - l), *Wn = WWr + 2 * (2 - l);
+                const R2 *V0n = Vr0 + (2 - l), *V1n = Vr1 + (2 - l);
+                R *S0o = Sr0 + (1 - l), *S1o = Sr1 + (1 - l);
+                const int c0 = on ? -lane : -(1 << 20);
+    #pragma unroll 2
+                for (int t = 0; t < STEPS; t++) {
+                    const R wv = __shfl_up_sync(0xffffffffu, last_new, 1);
+                    const bool act_ = (unsigned)(c0 + t) < (unsigned)NY;
+                    const R a0n = An[2 * t], a1n = An[2 * t + 1], w0n = Wn[2 * t], w1n = Wn[2 * t + 1];
+                    const R s0n = fma(hk, V0n[t].y, dky), s1n = fma(hk, V1n[t].y, dky);
+                    const R n0 = fma(w0, wv, p0);
+                    const R n1 = fma(w1, n0, p1);
+                    last_new = n1;
+                    if (act_) {
+                        S0o[t] = n0; S1o[t] = n1;
+                        p0 = fma(s0n, n0, a0n); p1 = fma(s1n, n1, a1n);
+                    }
+                    w0 = w0n; w1 = w1n;
+                }
+            }
+        };
+        // The sub-steps are software pipelined across the CTA's warps: the transport of sub-step it-1 is a one-warp
+        // recurrence (the wavefront, ~9 k cycles) and none of what follows it at the start of sub-step it needs the new
+        // T — the velocity ghost cells and the whole predictor up to the buoyancy term.  So while warp 0 runs the
+        // wavefront, the other warps apply the velocity boundary conditions (walls are not re-written: they stay zero
+        // and the wavefront reads them) and compute the predictor of THEIR tiles; after the barrier warp 0 catches up
+        // with the predictor of its tiles while the others set the T ghosts.  Before: 7 of 8 warps idle for 14 % of the
+        // kernel's time.
+        const int warp = tid >> 5;
+        for (int it = 0; it <= a.ndt_act; it++) {
+            // ---- stage X: transport of the previous sub-step || velocity BCs + predictor of this one ----------------
+            if (warp == 0) {
+                if (it > 0) wavefront();
+            } else if (it < a.ndt_act) {
+                bc_uv(tid - 32, T - 32, it == 0);
+                asm volatile("bar.sync 1, %0;" ::"r"(T - 32) : "memory");      // warps 1.. only: their ghost cells are in place
+                if (has_tile) predictor();
+            }
+            __syncthreads();                       // T is final; velocity ghosts final
             PHASE(0);
-
-            // ---- predictor into registers, rayleigh.py:371-407 -----------------------------------------
-            R us[TI][TJ], vs[TI][TJ];
-            if (has_tile) {
-                const R2 *uv = UV + ou;
-                const R *sc = S + ot, *p = gp + o;
-                // (u, v) pairs of the tile and its one-cell ring are fetched as 16-byte words where they are used (equal
-                // addresses are merged by the compiler)
+            if (it == a.ndt_act) break;
+            // ---- stage Y: warp 0 catches up (its tiles' predictor), the others set the T ghost cells ---------------
+            if (warp == 0) predictor();
+            else bc_s(tid - 32, T - 32);
+            if (has_tile) {                        // v* = v + dt (rhs + T), rayleigh.py:404 (T of the cell itself, no ghost)
                 TILE_LOOP {
-                    const R2 *q = uv + r * LDU + k;
-                    const R2 c = q[0], E = q[LDU], W = q[-LDU], Nn = q[1], Ss = q[-1];
-                    const R uc = c.x, vc = c.y, pc = p[r * LD + k];
-                    us[r][k] = uc; vs[r][k] = vc;
-                    if (r > 0 || !top) {               // i >= 2
-                        R uE = R(0.5) * (E.x + uc), uW = R(0.5) * (uc + W.x);
-                        R uN = R(0.5) * (Nn.x + uc), uS = R(0.5) * (uc + Ss.x);
-                        R vN = R(0.5) * (Nn.y + q[-LDU + 1].y), vS = R(0.5) * (vc + W.y);
-                        R conv = (uE * uE - uW * uW) * inv_dx + (uN * vN - uS * vS) * inv_dy;
-                        R diff = ((E.x - R(2) * uc + W.x) * a.inv_dx2 + (Nn.x - R(2) * uc + Ss.x) * a.inv_dy2) * a.dcoef;
-                        R pres = (pc - p[r * LD + k - LD]) * inv_dx;
-                        us[r][k] = uc + dt * (diff - conv - pres);
-                    }
-                    if (k > 0 || !lef) {               // j >= 2
-                        R vE = R(0.5) * (E.y + vc), vW = R(0.5) * (vc + W.y);
-                        R uE = R(0.5) * (E.x + q[LDU - 1].x), uW = R(0.5) * (uc + Ss.x);
-                        R vN = R(0.5) * (Nn.y + vc), vS = R(0.5) * (vc + Ss.y);
-                        R conv = (uE * vE - uW * vW) * inv_dx + (vN * vN - vS * vS) * inv_dy;
-                        R diff = ((E.y - R(2) * vc + W.y) * a.inv_dx2 + (Nn.y - R(2) * vc + Ss.y) * a.inv_dy2) * a.dcoef;
-                        R pres = (pc - p[r * LD + k - 1]) * inv_dy;
-                        vs[r][k] = vc + dt * (diff - conv - pres + sc[r * LDT + k]);
-                    }
+                    const R vc = UV[ou + r * LDU + k].y;
+                    vs[r][k] = (k > 0 || !lef) ? vc + dt * (vs[r][k] + S[ot + r * LDT + k]) : vc;
                 }
             }
             __syncthreads();                       // every read of the old u, v is done
@@ -933,10 +1027,6 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
             // LDS.128 fetches both rows of a lane and every address is base(lane) + 16*step.  The
             // west ghost row (i = 0, never updated) is folded into A of row 1 (B_W := 0 there).
             {
-                constexpr int RS = wavefront_row_stride(NY);       // columns 0..NY per row pair (0 unused), padded
-                static_assert(NX % 2 == 0 && NX / 2 <= 32, "wavefront layout: one lane per row pair");
-                static_assert(2 * (NX / 2) * RS <= NP, "wavefront planes must fit the exchange planes");
-                const R kx = a.tcoef * a.inv_dx2, ky = a.tcoef * a.inv_dy2;
                 if (has_tile) {
                     const R2 *uv = UV + ou;
                     const R *sc = S + ot;
@@ -957,51 +1047,6 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
                 }
                 __syncthreads();
                 PHASE(4);
-                if (tid < 32) {
-                    const R hk = R(0.5) * dt * inv_dy, dky = dt * ky;
-                    if constexpr (std::is_same<R, double>::value) {
-                        transport_wavefront_f64<NX, NY, LDU, LDT>((uint32_t)__cvta_generic_to_shared(PA), (uint32_t)__cvta_generic_to_shared(PB),
-                                                                  (uint32_t)__cvta_generic_to_shared(UV), (uint32_t)__cvta_generic_to_shared(S), hk, dky, tid);
-                    } else {
-                        // Lane l owns rows 2l+1, 2l+2 and does column j = t - l + 1 at step t.  The loop is
-                        // uniform: inactive steps (j outside 1..NY) compute on harmless in-bounds garbage and
-                        // are masked by ONE predicate (stores, partial sums); per step the dependent chain is
-                        // SHFL + 2 DFMA, the coefficients of column j+1 are fetched while it waits.
-                        constexpr int LANES = NX / 2, STEPS = NY + LANES - 1;
-                        const int lane = tid;
-                        const bool on = lane < LANES;
-                        const int l = on ? lane : 0;
-                        const R2 *Vr0 = UV + (2 * l + 1) * LDU, *Vr1 = Vr0 + LDU;
-                        R *Sr0 = S + (2 * l + 1) * LDT, *Sr1 = Sr0 + LDT;
-                        const R *AAr = PA + (size_t)l * RS * 2, *WWr = PB + (size_t)l * RS * 2;
-                        // column 1: partial sums with the south ghost (column 0, untouched by transport)
-                        R p0 = fma(fma(hk, Vr0[1].y, dky), Sr0[0], AAr[2]), p1 = fma(fma(hk, Vr1[1].y, dky), Sr1[0], AAr[3]);
-                        R w0 = WWr[2], w1 = WWr[3];
-                        R last_new = R(0);
-                        // pointers biased by -lane: element [t] is column t - lane + 2 (prefetch) / t - lane + 1 (store)
-                        // (lanes beyond the last row pair mimic lane 0 with the predicate off)
-                        const R *An = AAr + 2 * (2 - l), *Wn = WWr + 2 * (2 - l);
-                        const R2 *V0n = Vr0 + (2 - l), *V1n = Vr1 + (2 - l);
-                        R *S0o = Sr0 + (1 - l), *S1o = Sr1 + (1 - l);
-                        const int c0 = on ? -lane : -(1 << 20);
-    #pragma unroll 2
-                        for (int t = 0; t < STEPS; t++) {
-                            const R wv = __shfl_up_sync(0xffffffffu, last_new, 1);
-                            const bool act_ = (unsigned)(c0 + t) < (unsigned)NY;
-                            const R a0n = An[2 * t], a1n = An[2 * t + 1], w0n = Wn[2 * t], w1n = Wn[2 * t + 1];
-                            const R s0n = fma(hk, V0n[t].y, dky), s1n = fma(hk, V1n[t].y, dky);
-                            const R n0 = fma(w0, wv, p0);
-                            const R n1 = fma(w1, n0, p1);
-                            last_new = n1;
-                            if (act_) {
-                                S0o[t] = n0; S1o[t] = n1;
-                                p0 = fma(s0n, n0, a0n); p1 = fma(s1n, n1, a1n);
-                            }
-                            w0 = w0n; w1 = w1n;
-                        }
-                    }
-                }
-                __syncthreads();
                 PHASE(5);
             }
         }   // sub-steps
