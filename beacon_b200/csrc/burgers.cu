@@ -88,10 +88,14 @@ __global__ void __launch_bounds__(T) burgers_kernel(const BurArgs<R> a)
 #pragma unroll
             for (int m = 0; m < C + 1; m++) {
                 int f = a0 - 1 + m;
-                R r = fdiv(d[m], d[m + 1] + R(1.0e-8));
-                R phi = fdiv(r + rabs(r), R(1) + r);        // van Leer
-                if (f <= 0) phi = R(0);
-                F[m] = e[m + 1] + (R(0.5) * phi) * d[m + 1];
+                // van Leer, burgers.py:231-243: r = a / b, phi = (r + |r|) / (1 + r) with a = d[m], b = d[m+1] + 1e-8.
+                // In ONE division: a, b of equal sign -> phi / 2 = a / (a + b); opposite sign or a = 0 -> 0; a = -b
+                // (r = -1 exactly) -> NaN like the reference.  Halves the dependent division chain of the sub-step.
+                const R av = d[m], bv = d[m + 1] + R(1.0e-8), sum = av + bv;
+                R hphi = fdiv(av, sum);
+                if (!same_sign(av, bv)) hphi = is_zero(sum) ? qnan<R>() : R(0);    // sign / zero tests on the integer pipe
+                if (f <= 0) hphi = R(0);
+                F[m] = e[m + 1] + hphi * d[m + 1];
             }
 #pragma unroll
             for (int m = 0; m < C; m++) {
@@ -99,7 +103,7 @@ __global__ void __launch_bounds__(T) burgers_kernel(const BurArgs<R> a)
                 R du = (F[m + 1] - F[m]) * a.inv_dx;
                 R rhs = u[m] * du;                                                       // rhs(), :253-255
                 if (i == a.ctrl_pos) rhs += forcing;                                     // :149
-                if (i >= 1 && i <= nx - 2) u[m] = fdiv(R(4) * up[m] - upp[m] - a.two_dt * rhs, R(3));   // dert(), :247-249
+                if (i >= 1 && i <= nx - 2) u[m] = div3(R(4) * up[m] - upp[m] - a.two_dt * rhs);        // dert(), :247-249
             }
         };
         {

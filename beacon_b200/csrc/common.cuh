@@ -121,6 +121,23 @@ __device__ __forceinline__ double clamp0h(double hr)
 __device__ __forceinline__ float clamp0h(float hr) { return hr < 0.0f ? 0.0f : (hr > 0.5f ? 0.5f : hr); }
 __device__ __forceinline__ float fdiv(float a, float b) { return a / b; }
 
+// x / 3 without the reciprocal seed: q = x (1/3), one residual correction q += (x - 3 q)(1/3) — three dependent
+// fp64 instructions instead of MUFU + four (the quotient is within 1 ulp of the correctly rounded one)
+__device__ __forceinline__ double div3(double x)
+{
+    const double c = 1.0 / 3.0, q = x * c;
+    return fma(fma(-3.0, q, x), c, q);
+}
+__device__ __forceinline__ float div3(float x) { return x / 3.0f; }
+// sign / zero tests of floating-point values on the integer pipe (the fp64 pipe is the scarce resource)
+__device__ __forceinline__ bool same_sign(double a, double b) { return (__double2hiint(a) ^ __double2hiint(b)) >= 0; }
+__device__ __forceinline__ bool same_sign(float a, float b) { return (__float_as_int(a) ^ __float_as_int(b)) >= 0; }
+__device__ __forceinline__ bool is_zero(double a) { return ((__double2hiint(a) & 0x7fffffff) | __double2loint(a)) == 0; }
+__device__ __forceinline__ bool is_zero(float a) { return (__float_as_int(a) & 0x7fffffff) == 0; }
+template <typename R> __device__ __forceinline__ R qnan();
+template <> __device__ __forceinline__ double qnan<double>() { return __longlong_as_double(0x7ff8000000000000LL); }
+template <> __device__ __forceinline__ float qnan<float>() { return __int_as_float(0x7fc00000); }
+
 // Branch-free square root, same idea: MUFU.RSQ64H seed, two Newton steps on 1/sqrt(x), one
 // residual correction of sqrt(x); x = 0 is mapped to 0 by a select; negative / non-finite -> NaN.
 __device__ __forceinline__ double fsqrt(double x)

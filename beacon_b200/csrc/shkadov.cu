@@ -530,7 +530,7 @@ public:
         // measured on B200 (profiles/sweep_shkadov_r1j_*.txt): 10 jets (nx 1350) 6,256,2; 20 jets (nx 1850)
         // 10,192,2; 41 jets (nx 2900) 6,512,1
         BEACON_SHK_TRY(6, 256, 2)
-        if (wc) { BEACON_SHK_TRY(9, 160, 3) BEACON_SHK_TRY(9, 160, 2) BEACON_SHK_TRY(11, 128, 3) BEACON_SHK_TRY(11, 128, 2) }   // tuning only
+        if (wc) { BEACON_SHK_TRY(9, 160, 3) BEACON_SHK_TRY(9, 160, 2) BEACON_SHK_TRY(11, 128, 3) BEACON_SHK_TRY(11, 128, 2) BEACON_SHK_TRY(5, 640, 1) BEACON_SHK_TRY(10, 320, 1) }   // tuning only
         BEACON_SHK_TRY(10, 192, 2)
         BEACON_SHK_TRY(6, 512, 1)
         BEACON_SHK_TRY(12, 512, 1)

@@ -15,8 +15,8 @@ class VectorEnv:
     episode).  shkadov envs restart with a random number of warm steps U{0..rand_steps}
     (shkadov.py:118-123) drawn from a seeded device generator."""
 
-    def __init__(self, name, num_envs, auto_reset=True, rand_init=True, rand_steps=400, seed=0, **kwargs):
-        self.env = BatchedEnv(name, batch=num_envs, seed=seed, **kwargs)
+    def __init__(self, name, num_envs, auto_reset=True, rand_init=True, rand_steps=400, seed=0, device=0, **kwargs):
+        self.env = BatchedEnv(name, batch=num_envs, seed=seed, device=device, **kwargs)
         self.name, self.num_envs, self.auto_reset = name, num_envs, auto_reset
         self.rand_init, self.rand_steps = rand_init and name == "shkadov", rand_steps
         self._gen = torch.Generator(device=self.env.device)

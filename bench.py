@@ -490,7 +490,8 @@ def run_workload(wl, B, K, W, cx, args, headline):
                   "peer_epilogue": {"value": N * K / t_peer, "unit": "env-actions/s",
                                     "what": "step kernel writes each env's obs / rwd / flag rows into the learner GPU's buffer over NVLink "
                                             "(CUDA IPC mapping), then a 4-byte all-reduce as the completion fence"},
-                  "bytes_to_learner_per_step": int((world - 1) * B * (env.n_obs * 8 + env.rwd_dim * 8 + 2))}
+                  "bytes_to_learner_per_step": int((world - 1) * B * (env.n_obs * 8 + env.rwd_dim * 8 + 2)),
+                  "note": "back-to-back steps, no L2 flush between them (unlike `value`): compare the two gather variants with each other"}
 
     if rank != 0:
         return None
@@ -544,6 +545,33 @@ def run_workload(wl, B, K, W, cx, args, headline):
     if gather:
         res["e2e_gather"] = gather
     return res
+
+
+def run_vector_episode(cx, args, B=1024, steps=440):
+    """What an agent actually drives: VectorEnv (auto-reset, U{0..400} warm steps per restarted env as in
+    shkadov.py:118-123) over more than one 400-action episode, resets included, no host sync in the loop."""
+    torch = cx.torch
+    from beacon_b200.vector import VectorEnv
+    dev = cx.dev
+    v = VectorEnv("shkadov", B, n_jets=10, seed=1234, device=cx.local)
+    g = torch.Generator(device=dev); g.manual_seed(11)
+    acts = torch.rand(8, B, 10, generator=g, device=dev, dtype=torch.float64) * 2 - 1
+    v.reset()
+    for k in range(3):
+        v.step(acts[k])
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_done = torch.zeros((), dtype=torch.int64, device=dev)
+    a.record()
+    for k in range(steps):
+        obs, rwd, done, trunc, info = v.step(acts[k % 8])
+        n_done += done.sum()
+    b.record()
+    torch.cuda.synchronize()
+    t = a.elapsed_time(b) * 1e-3
+    return {"value": B * steps / t, "unit": "env-actions/s (agent-visible steps; the warm steps of the restarts are extra work inside the same time)",
+            "steps": steps, "envs_per_gpu": B, "episodes_finished": int(n_done.item()), "seconds": t,
+            "config": {"workload": "VectorEnv('shkadov', 1024, n_jets=10): auto-reset with U{0..400} zero-action warm steps, one masked reset launch per step"}}
 
 
 def run_burgers_single(cx, args, K=200):
@@ -642,6 +670,10 @@ def main():
                     workloads["burgers_single_env"] = run_burgers_single(cx, args)
                 except Exception as e:
                     workloads["burgers_single_env"] = {"error": repr(e)[:300]}
+                try:
+                    workloads["shkadov_vector_env_episode"] = run_vector_episode(cx, args)
+                except Exception as e:
+                    workloads["shkadov_vector_env_episode"] = {"error": repr(e)[:300]}
             continue
         K2 = min(K2, args.steps) if args.steps else K2
         K2 = max(K2, 3)
