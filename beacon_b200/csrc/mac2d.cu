@@ -821,20 +821,36 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
         // kernel's time.
         const int warp = tid >> 5;
         for (int it = 0; it <= a.ndt_act; it++) {
-            // ---- stage X: transport of the previous sub-step || velocity BCs + predictor of this one ----------------
-            if (warp == 0) {
-                if (it > 0) wavefront();
-            } else if (it < a.ndt_act) {
-                bc_uv(tid - 32, T - 32, it == 0);
-                asm volatile("bar.sync 1, %0;" ::"r"(T - 32) : "memory");      // warps 1.. only: their ghost cells are in place
-                if (has_tile) predictor();
+            // stage X: transport of the previous sub-step (warp 0) || velocity BCs + predictor of this one (the others);
+            // stage Y: warp 0 catches up with the predictor of its tiles, the others set the T ghost cells.
+            // One two-trip loop so that the predictor exists ONCE in the instruction stream.
+            bool last = false;
+#pragma unroll 1
+            for (int stage = 0; stage < 2; stage++) {
+                bool pred;
+                if (stage == 0) {
+                    if (warp == 0) {
+                        if (it > 0) wavefront();
+                        pred = false;
+                    } else {
+                        pred = it < a.ndt_act;
+                        if (pred) {
+                            bc_uv(tid - 32, T - 32, it == 0);
+                            asm volatile("bar.sync 1, %0;" ::"r"(T - 32) : "memory");   // warps 1.. only: their ghost cells are in place
+                        }
+                    }
+                } else {
+                    pred = warp == 0;
+                    if (!pred) bc_s(tid - 32, T - 32);
+                }
+                if (pred && has_tile) predictor();
+                if (stage == 0) {
+                    __syncthreads();               // T is final; velocity ghosts final
+                    PHASE(0);
+                    if (it == a.ndt_act) { last = true; break; }
+                }
             }
-            __syncthreads();                       // T is final; velocity ghosts final
-            PHASE(0);
-            if (it == a.ndt_act) break;
-            // ---- stage Y: warp 0 catches up (its tiles' predictor), the others set the T ghost cells ---------------
-            if (warp == 0) predictor();
-            else bc_s(tid - 32, T - 32);
+            if (last) break;
             if (has_tile) {                        // v* = v + dt (rhs + T), rayleigh.py:404 (T of the cell itself, no ghost)
                 TILE_LOOP {
                     const R vc = UV[ou + r * LDU + k].y;

@@ -125,7 +125,7 @@ def unit_model(wl, d, sweeps_per_action, census):
         warps = 8 if wl == "rayleigh" else 16
         sw, ot, wf = c["per_sweep"], c["substep_other"], c["wavefront_loop"]
         nd = d["ndt_act"]
-        trips = (13 if wl == "rayleigh" else 2 * 13) * nd      # wavefront: 6 columns per trip, one warp
+        trips = (13 if wl == "rayleigh" else 2 * 21) * nd      # wavefront: 6 columns per trip, one warp (mixing: two row passes of 126 steps)
         fp64 = warps * (sweeps_per_action * sw["fp64"] + nd * ot["fp64"]) + trips * wf["fp64"]
         smem = warps * (sweeps_per_action * sw.get("smem_wavefronts", 0) + nd * ot.get("smem_wavefronts", 0)) + trips * wf.get("smem_wavefronts", 0)
         return {"fp64": fp64, "smem": smem,

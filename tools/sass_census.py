@@ -120,7 +120,10 @@ def census():
         name, ins = find(f, *needles)
         ls = loops_of(ins)
         stats = [(lo, hi, count(ins, lo, hi)) for lo, hi in ls]
-        sweeps = [s for s in stats if s[2].get("bar", 0) == 2 and s[2].get("fp64", 0) >= 60 and
+        def bfly(lo, hi):
+            return sum(1 for i in range(lo, hi + 1) if ins[i][1].split()[0 if not ins[i][1].startswith("@") else 1].startswith("SHFL.BFLY"))
+        # the sweep loop: two CTA barriers per trip, the butterfly shuffles of the residual reduction, no inner barrier loop
+        sweeps = [s for s in stats if s[2].get("bar", 0) == 2 and s[2].get("fp64", 0) >= 60 and bfly(s[0], s[1]) >= 8 and
                   not any(o[0] >= s[0] and o[1] <= s[1] and (o[0], o[1]) != (s[0], s[1]) and o[2].get("bar", 0) for o in stats)]
         sw = max(sweeps, key=lambda s: s[2]["fp64"])
         outer = min((s for s in stats if s[0] <= sw[0] and s[1] >= sw[1] and (s[0], s[1]) != (sw[0], sw[1])), key=lambda s: s[1] - s[0])

@@ -16,6 +16,8 @@ KEYS = [
     "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "sm__cycles_elapsed.max",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
     "smsp__sass_inst_executed_op_local_ld.sum", "smsp__sass_inst_executed_op_local_st.sum",
+    "smsp__inst_executed_pipe_fp64.sum", "sm__inst_executed_pipe_fp64.sum", "smsp__inst_executed_op_shared_ld.sum",
+    "smsp__inst_executed_op_shared_st.sum", "sm__cycles_active.avg", "smsp__cycles_active.avg",
 ]
 
 rep, out = sys.argv[1], sys.argv[2]
