@@ -64,10 +64,10 @@ def build(force=False, verbose=False, tag=None, defines=()):
         if res.returncode != 0:
             raise RuntimeError("link failed: %s\n%s" % (" ".join(cmd), res.stderr))
     census = os.path.join(LIBDIR, "sass_census.json")
-    if not tag and (jobs or force or _stale(census, objs)):
+    tool = os.path.join(HERE, "..", "tools", "sass_census.py")
+    if not tag and (jobs or force or _stale(census, objs + [tool])):
         # static SASS census of the hot loops (fp64 / shared-memory instructions per sub-step and per Jacobi sweep):
         # bench.py turns it into the in-run roofline fraction
-        tool = os.path.join(HERE, "..", "tools", "sass_census.py")
         res = subprocess.run([sys.executable, tool, census], capture_output=True, text=True)
         if res.returncode != 0:
             print("sass census failed (bench.py will report the S-model only):\n" + res.stderr[-2000:], file=sys.stderr)

@@ -88,3 +88,18 @@ def test_philox_reference_vector():
     assert philox([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
     assert philox([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
         [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_sass_census_identifies_the_hot_loops():
+    """bench.py's in-run roofline multiplies these static per-loop counts by the run's trip counts: a wrong loop
+    pick (e.g. a barrier loop that is not the Jacobi sweep) must not go unnoticed."""
+    from beacon_b200 import build
+    build.build()
+    c = json.load(open(os.path.join(ROOT, "beacon_b200", "lib", "sass_census.json")))
+    shk = c["shkadov_6_256_2"]["substep_unrolled2"]["per_substep"]
+    assert 240 <= shk["fp64"] <= 320 and shk["instr"] < 700, shk
+    for tag, cells in (("rayleigh_reg", 10), ("mixing_big", 20)):
+        sw = c[tag]["per_sweep"]
+        assert sw["bar"] == 1.0 and 6 * cells <= sw["fp64"] <= 9 * cells, (tag, sw)          # 6 fp64 per cell + the tile residual
+        assert 4 * cells <= sw["smem_wavefronts"] <= 8 * cells, (tag, sw)
+        assert c[tag]["substep_other"]["fp64"] > 5 * sw["fp64"] and c[tag]["wavefront_loop"]["fp64"] >= 12
