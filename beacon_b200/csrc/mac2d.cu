@@ -567,6 +567,11 @@ __device__ __noinline__ bool residual_converged_exact(R mine, R *s_exact, R tol)
 // half-warp fall into 16 distinct 8-byte banks iff (TI * LDP) mod 16 == 2 (TI = 2: 57, TI = 5: 58).
 constexpr int mac_ldp(int ld, int ti) { int l = ld; while ((ti * l) % 16 != 2) l++; return l; }
 
+#ifdef MAC_CLUSTER_BARRIER_TEST
+#define SWEEP_BARRIER() asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory")
+#else
+#define SWEEP_BARRIER() __syncthreads()
+#endif
 template <typename R, int NX, int NY, int TI, int TJ, int T, bool DBG>
 __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
 {
@@ -1003,7 +1008,7 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
                     if (converged(err, accq)) { itp = k - 2; pf = pb; break; }
                     commit(phi, pb);
                     if ((tid & 31) == 0) s_part[0][tid >> 5] = ws;
-                    __syncthreads();
+                    SWEEP_BARRIER();
                     accq = accp; accp = acc;
                 }
                 {   // even k+1: phi_k (in PB) -> phi_{k+1}; decide on sweep k-1 (still in PA)
@@ -1014,7 +1019,7 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
                     if (converged(err, accq)) { itp = k - 1; pf = pa; break; }
                     commit(phi, pa);
                     if ((tid & 31) == 0) s_part[1][tid >> 5] = ws;
-                    __syncthreads();
+                    SWEEP_BARRIER();
                     accq = accp; accp = acc;
                 }
             }
@@ -1793,7 +1798,18 @@ public:
             BEACON_CUDA_CHECK(cudaMemsetAsync(dbgbuf.ptr, 0, 64, st));
             a.dbg = dbgbuf.as<unsigned long long>();
         }
+#ifdef MAC_CLUSTER_BARRIER_TEST
+        {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(a.B); cfg.blockDim = dim3(T); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            BEACON_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, a));
+        }
+#else
         kernel<<<a.B, T, smem, st>>>(a);
+#endif
         BEACON_CUDA_CHECK(cudaGetLastError());
         launches++;
         if (debug && dbg_variant && a.mode == 0) {
