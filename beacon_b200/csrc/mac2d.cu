@@ -1051,6 +1051,7 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
                 if (has_tile) {
                     const R2 *uv = UV + ou;
                     const R *sc = S + ot;
+                    R Av[TI][TJ], Wv[TI][TJ];
                     TILE_LOOP {
                         const int e = r * LDT + k;
                         const R2 c = uv[r * LDU + k];
@@ -1061,9 +1062,24 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
                         R A = s0 + dt * (diff0 - conv0);
                         R BW = dt * (kx + R(0.5) * uW * inv_dx);
                         if (r == 0 && top) { A = fma(BW, sc[e - LDT], A); BW = R(0); }
-                        const int gi = TI * ti + r, idx = ((gi >> 1) * RS + j0 + k) * 2 + (gi & 1);   // [row pair][column][row in pair]
-                        PA[idx] = A;
-                        PB[idx] = BW;
+                        Av[r][k] = A; Wv[r][k] = BW;
+                    }
+                    // [row pair][column][row in pair]: with two-row tiles the two rows of a column are ONE 16-byte slot
+                    // (conflict free for a quarter-warp: 58 ti + 5 tj mod 8 is a permutation); other tile heights store
+                    // element by element
+                    if constexpr (TI == 2) {
+                        R2 *A2 = reinterpret_cast<R2 *>(PA) + ti * RS + j0, *W2 = reinterpret_cast<R2 *>(PB) + ti * RS + j0;
+#pragma unroll
+                        for (int k = 0; k < TJ; k++) {
+                            R2 x; x.x = Av[0][k]; x.y = Av[1][k]; A2[k] = x;
+                            R2 y; y.x = Wv[0][k]; y.y = Wv[1][k]; W2[k] = y;
+                        }
+                    } else {
+                        TILE_LOOP {
+                            const int gi = TI * ti + r, idx = ((gi >> 1) * RS + j0 + k) * 2 + (gi & 1);
+                            PA[idx] = Av[r][k];
+                            PB[idx] = Wv[r][k];
+                        }
                     }
                 }
                 __syncthreads();
