@@ -735,9 +735,9 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
                 }
             }
         };
-        // ---- predictor into registers, rayleigh.py:371-407: us = u*, vx = the right-hand side of v* WITHOUT the
-        // buoyancy term (v* = v + dt (vx + T) is formed later with the transported T: the same operations in the same
-        // order as the reference's expression)
+        // ---- predictor into registers, rayleigh.py:371-407: the right-hand sides of u* and v* (v: WITHOUT the buoyancy
+        // term); u* = u + dt rhs_u and v* = v + dt (rhs_v + T) are formed later with the transported T: the same
+        // operations in the same order as the reference's expressions
         R us[TI][TJ], vs[TI][TJ];
         auto predictor = [&]() {
             const R2 *uv = UV + ou;
@@ -748,7 +748,7 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
                 const R2 *q = uv + r * LDU + k;
                 const R2 c = q[0], E = q[LDU], W = q[-LDU], Nn = q[1], Ss = q[-1];
                 const R uc = c.x, vc = c.y, pc = p[r * LD + k];
-                us[r][k] = uc; vs[r][k] = R(0);
+                us[r][k] = R(0); vs[r][k] = R(0);
                 if (r > 0 || !top) {               // i >= 2
                     R uE = R(0.5) * (E.x + uc), uW = R(0.5) * (uc + W.x);
                     R uN = R(0.5) * (Nn.x + uc), uS = R(0.5) * (uc + Ss.x);
@@ -756,7 +756,7 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
                     R conv = (uE * uE - uW * uW) * inv_dx + (uN * vN - uS * vS) * inv_dy;
                     R diff = ((E.x - R(2) * uc + W.x) * a.inv_dx2 + (Nn.x - R(2) * uc + Ss.x) * a.inv_dy2) * a.dcoef;
                     R pres = (pc - p[r * LD + k - LD]) * inv_dx;
-                    us[r][k] = uc + dt * (diff - conv - pres);
+                    us[r][k] = diff - conv - pres;
                 }
                 if (k > 0 || !lef) {               // j >= 2
                     R vE = R(0.5) * (E.y + vc), vW = R(0.5) * (vc + W.y);
@@ -856,10 +856,11 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
                 }
             }
             if (last) break;
-            if (has_tile) {                        // v* = v + dt (rhs + T), rayleigh.py:404 (T of the cell itself, no ghost)
-                TILE_LOOP {
-                    const R vc = UV[ou + r * LDU + k].y;
-                    vs[r][k] = (k > 0 || !lef) ? vc + dt * (vs[r][k] + S[ot + r * LDT + k]) : vc;
+            if (has_tile) {                        // u* = u + dt rhs_u, v* = v + dt (rhs_v + T), rayleigh.py:393,404
+                TILE_LOOP {                        // (T of the cell itself, no ghost; the pair is one conflict-free 16-byte load)
+                    const R2 c = UV[ou + r * LDU + k];
+                    us[r][k] = (r > 0 || !top) ? c.x + dt * us[r][k] : c.x;
+                    vs[r][k] = (k > 0 || !lef) ? c.y + dt * (vs[r][k] + S[ot + r * LDT + k]) : c.y;
                 }
             }
             __syncthreads();                       // every read of the old u, v is done
