@@ -1600,22 +1600,35 @@ __global__ void __launch_bounds__(T, MINB) mac_big_kernel(const MacArgs<R> a)
                 for (int ps = 0; ps < PASSES; ps++) {
                     const int ib = 1 + ps * PASS_ROWS, ie = min(NX, ib + PASS_ROWS - 1);
                     const bool mine = has_tile && i0 >= ib && i0 <= ie;       // passes are tile aligned
+                    typedef typename vec2_of<R>::type R2;
+                    static_assert(TI % 2 == 0 && PASS_ROWS % 2 == 0, "row pairs of a tile are whole wavefront slots");
+                    // [row pair][column][row in pair]: the two rows of a pair are ONE 16-byte slot (tiles are an even number
+                    // of rows high and passes start on tile boundaries): half the store instructions, conflict free
+                    R2 *A2 = reinterpret_cast<R2 *>(AA) + ((i0 - ib) >> 1) * RS + j0, *W2 = reinterpret_cast<R2 *>(WW) + ((i0 - ib) >> 1) * RS + j0,
+                       *S2 = reinterpret_cast<R2 *>(SS) + ((i0 - ib) >> 1) * RS + j0;
                     if (mine) {
                         const R *uu = u + o, *vv = v + o, *sc = s + o;
-                        TILE_LOOP {
-                            const int e = r * LD + k;
-                            const R uE = uu[e + LD], uW = uu[e], vN = vv[e + 1], vS = vv[e];
-                            const R s0 = sc[e], sE = sc[e + LD], sN = sc[e + 1];
-                            R diff0 = ((sE - R(2) * s0) * a.inv_dx2 + (sN - R(2) * s0) * a.inv_dy2) * a.tcoef;
-                            R conv0 = (uE * (R(0.5) * (sE + s0)) - uW * (R(0.5) * s0)) * inv_dx + (vN * (R(0.5) * (sN + s0)) - vS * (R(0.5) * s0)) * inv_dy;
-                            R A = s0 + dt * (diff0 - conv0);
-                            R BW = dt * (kx + R(0.5) * uW * inv_dx);
-                            R BS = dt * (ky + R(0.5) * vS * inv_dy);
-                            if (k == 0 && lef) { A = fma(BS, sc[e - 1], A); BS = R(0); }                 // south ghost column
-                            if (r == 0 && i0 == ib) { A = fma(BW, sc[e - LD], A); BW = R(0); }           // row west of the pass
-                            const int idx = (((i0 - ib + r) >> 1) * RS + j0 + k) * 2 + ((i0 - ib + r) & 1);
-                            AA[idx] = A; WW[idx] = BW; SS[idx] = BS;
-                        }
+#pragma unroll
+                        for (int rp = 0; rp < TI; rp += 2)
+#pragma unroll
+                            for (int k = 0; k < TJ; k++) {
+                                R2 xa, xw, xs;
+#pragma unroll
+                                for (int q = 0; q < 2; q++) {
+                                    const int r = rp + q, e = r * LD + k;
+                                    const R uE = uu[e + LD], uW = uu[e], vN = vv[e + 1], vS = vv[e];
+                                    const R s0 = sc[e], sE = sc[e + LD], sN = sc[e + 1];
+                                    R diff0 = ((sE - R(2) * s0) * a.inv_dx2 + (sN - R(2) * s0) * a.inv_dy2) * a.tcoef;
+                                    R conv0 = (uE * (R(0.5) * (sE + s0)) - uW * (R(0.5) * s0)) * inv_dx + (vN * (R(0.5) * (sN + s0)) - vS * (R(0.5) * s0)) * inv_dy;
+                                    R A = s0 + dt * (diff0 - conv0);
+                                    R BW = dt * (kx + R(0.5) * uW * inv_dx);
+                                    R BS = dt * (ky + R(0.5) * vS * inv_dy);
+                                    if (k == 0 && lef) { A = fma(BS, sc[e - 1], A); BS = R(0); }                 // south ghost column
+                                    if (r == 0 && i0 == ib) { A = fma(BW, sc[e - LD], A); BW = R(0); }           // row west of the pass
+                                    if (q == 0) { xa.x = A; xw.x = BW; xs.x = BS; } else { xa.y = A; xw.y = BW; xs.y = BS; }
+                                }
+                                A2[(rp >> 1) * RS + k] = xa; W2[(rp >> 1) * RS + k] = xw; S2[(rp >> 1) * RS + k] = xs;
+                            }
                     }
                     __syncthreads();
                     PHASE(4);
@@ -1623,10 +1636,13 @@ __global__ void __launch_bounds__(T, MINB) mac_big_kernel(const MacArgs<R> a)
                     __syncthreads();
                     PHASE(5);
                     if (mine) {
-                        TILE_LOOP {
-                            const int idx = (((i0 - ib + r) >> 1) * RS + j0 + k) * 2 + ((i0 - ib + r) & 1);
-                            s[o + r * LD + k] = AA[idx];
-                        }
+#pragma unroll
+                        for (int rp = 0; rp < TI; rp += 2)
+#pragma unroll
+                            for (int k = 0; k < TJ; k++) {
+                                const R2 x = A2[(rp >> 1) * RS + k];
+                                s[o + rp * LD + k] = x.x; s[o + (rp + 1) * LD + k] = x.y;
+                            }
                     }
                     __syncthreads();
                     PHASE(6);
