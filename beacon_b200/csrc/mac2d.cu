@@ -1175,6 +1175,17 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
 // overwrite A in place.  Per step: 3 x 16-byte loads, 2 shuffles, 4 FMAs, one predicated store.
 // ---------------------------------------------------------------------------------------
 
+__device__ __forceinline__ double2 lds_pair(const double2 *p)
+{
+    return lds128_f64((uint32_t)__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ float2 lds_pair(const float2 *p)
+{
+    float2 v;
+    asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+    return v;
+}
+
 template <typename R, int NY>
 __device__ __noinline__ void transport_wavefront3(uint32_t offA, uint32_t offW, uint32_t offS, int lanes, int lane)
 {
@@ -1195,7 +1206,11 @@ __device__ __noinline__ void transport_wavefront3(uint32_t offA, uint32_t offW, 
     const int steps = ((NY + lanes - 1 + 5) / 6) * 6;   // padded: the extra steps are masked, their reads stay in shared memory
 #pragma unroll 6
     for (int t = 0; t < steps; t++) {
-        const R2 an2 = An[t + 1], wn2 = Wn[t + 1], sn2 = Sn[t + 1];     // two columns ahead
+        // two columns ahead.  Plain (non-volatile) asm loads: a lane never reads a slot of its own row pair that it has
+        // stored (loads run two columns ahead of the stores), so they may be hoisted over the C++ stores below; as C++
+        // loads of the same array they were ordered behind the previous step's store and their latency sat in the
+        // dependent chain: 81 -> 48 cycles per step in isolation (tools/micro/wave.cu)
+        const R2 an2 = lds_pair(An + t + 1), wn2 = lds_pair(Wn + t + 1), sn2 = lds_pair(Sn + t + 1);
         const R wv = __shfl_up_sync(0xffffffffu, last_new, 1);
         const R n0 = fma(w0, wv, p0);
         const R n1 = fma(w1, n0, p1);
