@@ -1555,6 +1555,7 @@ __global__ void __launch_bounds__(T, MINB) mac_big_kernel(const MacArgs<R> a)
             }
             int itp;
             const R *pf;                                  // plane holding the final iterate (tile-relative)
+#ifdef MAC_BIG_DECIDE_LAST
             for (int k = 3;; k += 2) {
                 {   // odd k: phi_{k-1} (in PA) -> phi_k; decide on sweep k-2 (still in PB)
                     float ws = (float)accp;
@@ -1579,6 +1580,71 @@ __global__ void __launch_bounds__(T, MINB) mac_big_kernel(const MacArgs<R> a)
                     accq = accp; accp = acc;
                 }
             }
+#else
+            // One CTA per SM: nobody fills the gaps of a sweep, so the tile stores must overlap the arithmetic.  The
+            // stores of sweep k overwrite phi_{k-2}, which a converged solve returns — hence the decision on sweep k-2
+            // (partials published at the previous barrier) is taken EARLY, after the first tile column, and every
+            // column is stored as soon as it is computed.  Compared with deciding after the sweep (mac_reg_kernel,
+            // where a second CTA hides the store phase and the exposed decision latency cost more than it won) a
+            // converged solve also drops one speculative sweep instead of two.  Same decisions, same sweep counts.
+            auto iter = [&](const R *pi, R *po, const float *part_rd, float *part_wr, const int kdec) -> int {
+                float wsum = (float)accp;
+                R rs[TI], po_[TI], cl = R(0), cr = R(0);
+                const R *pn = pi + o_n, *ps = pi + o_s;
+#pragma unroll
+                for (int r = 0; r < TI; r++) { rs[r] = R(0); const R hw = pi[r * LDP - 1]; po_[r] = lefx ? phi[r][0] : hw; }
+#pragma unroll
+                for (int k = 0; k < TJ; k++) {
+                    if (k < 5) wsum += __shfl_xor_sync(0xffffffffu, wsum, 16 >> k);
+                    const R hnk = pn[k], hsk = ps[k];
+                    R old[TI];
+#pragma unroll
+                    for (int r = 0; r < TI; r++) old[r] = phi[r][k];
+#pragma unroll
+                    for (int r = 0; r < TI; r++) {
+                        const R xm = (r > 0) ? old[r - 1] : hnk, xp = (r < TI - 1) ? old[r + 1] : hsk;
+                        R yp;
+                        if (k < TJ - 1) yp = phi[r][k + 1];
+                        else { const R he = pi[r * LDP + TJ]; yp = dir_e ? R(0) : (rigx ? old[r] : he); }
+                        const R ym = po_[r];
+                        const R nv = fma(xp + xm, a.pk1, fma(yp + ym, a.pk2, cn[r][k]));
+                        const R d = nv - old[r];
+                        rs[r] = fma(d, d, rs[r]);
+                        if (k == 0) cl = fma(d, d, cl);
+                        if (k == TJ - 1) cr = fma(d, d, cr);
+                        phi[r][k] = nv;
+                        po_[r] = old[r];
+                    }
+                    if (k == 0) {                 // sweep kdec = k - 2: converged?  (nothing of phi_{k-2} has been overwritten yet)
+                        const float err = total32(part_rd);
+                        if (kdec > a.itmax) return 2;
+                        if (converged(err, accq)) return 1;
+                    }
+                    if (has_tile) {
+#pragma unroll
+                        for (int r = 0; r < TI; r++) po[r * LDP + k] = phi[r][k];
+                    }
+                }
+#pragma unroll
+                for (int st = TJ; st < 5; st++) wsum += __shfl_xor_sync(0xffffffffu, wsum, 16 >> st);
+                R mid = R(0);
+#pragma unroll
+                for (int r = 1; r < TI - 1; r++) mid += rs[r];
+                const R acc0 = (TI > 1) ? fma(rs[0], w_top, fma(rs[TI - 1], w_bot, mid)) : rs[0] * (w_top + w_bot - R(1));
+                const R acc = fma(cl, w_lef, fma(cr, w_rig, acc0)) * w_has;
+                if ((tid & 31) == 0) part_wr[tid >> 5] = wsum;
+                __syncthreads();
+                accq = accp; accp = acc;
+                return 0;
+            };
+            for (int k = 3;; k += 2) {
+                // odd k: phi_{k-1} (in PA) -> phi_k (into PB, which holds phi_{k-2} until the decision on it is taken)
+                int st = iter(pa, pb, s_part[1], s_part[0], k - 2);
+                if (st) { if (st == 2) status |= BEACON_STATUS_POISSON_OVERFLOW; itp = k - 2; pf = pb; break; }
+                st = iter(pb, pa, s_part[0], s_part[1], k - 1);
+                if (st) { if (st == 2) status |= BEACON_STATUS_POISSON_OVERFLOW; itp = k - 1; pf = pa; break; }
+            }
+#endif
             TILE_LOOP { phi[r][k] = pf[r * LDP + k]; }     // the converged iterate
             it_total += itp;
             PHASE(2);

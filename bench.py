@@ -127,10 +127,14 @@ def unit_model(wl, d, sweeps_per_action, census):
         nd = d["ndt_act"]
         trips = (13 if wl == "rayleigh" else 2 * 21) * nd      # wavefront: 6 columns per trip, one warp (mixing: two row passes of 126 steps)
         fp64 = warps * (sweeps_per_action * sw["fp64"] + nd * ot["fp64"]) + trips * wf["fp64"]
-        smem = warps * (sweeps_per_action * sw.get("smem_wavefronts", 0) + nd * ot.get("smem_wavefronts", 0)) + trips * wf.get("smem_wavefronts", 0)
+        # sweep loop: predicated wavefronts count too (the tile stores of the big kernel are predicated on "thread owns a
+        # tile", true for 500 of 512 threads); elsewhere predicated = ghost-cell copies of a few boundary threads, left out
+        sw_smem = sw.get("smem_wavefronts", 0) + sw.get("smem_wavefronts_pred", 0)
+        smem = warps * (sweeps_per_action * sw_smem + nd * ot.get("smem_wavefronts", 0)) + trips * wf.get("smem_wavefronts", 0)
         return {"fp64": fp64, "smem": smem,
-                "how": f"{warps} warps x ({sweeps_per_action:.0f} sweeps x {sw['fp64']:.0f} fp64 / {sw.get('smem_wavefronts', 0):.0f} smem wavefronts per sweep + "
-                       f"{nd} sub-steps x {ot['fp64']} / {ot.get('smem_wavefronts', 0)}) + one-warp transport wavefront; unpredicated, conflict-free wavefronts (lower bound)"}
+                "how": f"{warps} warps x ({sweeps_per_action:.0f} sweeps x {sw['fp64']:.0f} fp64 / {sw_smem:.0f} smem wavefronts per sweep + "
+                       f"{nd} sub-steps x {ot['fp64']} / {ot.get('smem_wavefronts', 0)}) + one-warp transport wavefront; conflict-free wavefronts, counted "
+                       f"sweeps only (speculative ones excluded): a lower bound"}
     return None
 
 
