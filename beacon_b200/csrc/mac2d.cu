@@ -1583,16 +1583,23 @@ __global__ void __launch_bounds__(T, MINB) mac_big_kernel(const MacArgs<R> a)
 #else
             // One CTA per SM: nobody fills the gaps of a sweep, so the tile stores must overlap the arithmetic.  The
             // stores of sweep k overwrite phi_{k-2}, which a converged solve returns — hence the decision on sweep k-2
-            // (partials published at the previous barrier) is taken EARLY, after the first tile column, and every
-            // column is stored as soon as it is computed.  Compared with deciding after the sweep (mac_reg_kernel,
-            // where a second CTA hides the store phase and the exposed decision latency cost more than it won) a
-            // converged solve also drops one speculative sweep instead of two.  Same decisions, same sweep counts.
+            // (partials published at the previous barrier) is taken FIRST, right after the west halo loads are issued,
+            // and every tile column is stored as soon as it is computed.  Compared with deciding after the sweep
+            // (mac_reg_kernel, where a second CTA hides the store phase and the exposed decision latency cost more than
+            // it won) a converged solve also drops one speculative sweep instead of two.  Same decisions, same sweep
+            // counts.  Where exactly the decision sits matters through the register allocation: taken after the first
+            // column it left 14 spilled doubles per sweep in the loop (3.81 k env-actions/s), here 5 (4.09 k).
             auto iter = [&](const R *pi, R *po, const float *part_rd, float *part_wr, const int kdec) -> int {
                 float wsum = (float)accp;
-                R rs[TI], po_[TI], cl = R(0), cr = R(0);
+                R rt = R(0), rb = R(0), rm = R(0), po_[TI], cl = R(0), cr = R(0);   // residual: first / last / middle tile rows
                 const R *pn = pi + o_n, *ps = pi + o_s;
 #pragma unroll
-                for (int r = 0; r < TI; r++) { rs[r] = R(0); const R hw = pi[r * LDP - 1]; po_[r] = lefx ? phi[r][0] : hw; }
+                for (int r = 0; r < TI; r++) { const R hw = pi[r * LDP - 1]; po_[r] = lefx ? phi[r][0] : hw; }
+                {                                 // sweep kdec = k - 2: converged?  (nothing of phi_{k-2} has been overwritten yet)
+                    const float err = total32(part_rd);
+                    if (kdec > a.itmax) return 2;
+                    if (converged(err, accq)) return 1;
+                }
 #pragma unroll
                 for (int k = 0; k < TJ; k++) {
                     if (k < 5) wsum += __shfl_xor_sync(0xffffffffu, wsum, 16 >> k);
@@ -1609,16 +1616,11 @@ __global__ void __launch_bounds__(T, MINB) mac_big_kernel(const MacArgs<R> a)
                         const R ym = po_[r];
                         const R nv = fma(xp + xm, a.pk1, fma(yp + ym, a.pk2, cn[r][k]));
                         const R d = nv - old[r];
-                        rs[r] = fma(d, d, rs[r]);
+                        if (r == 0) rt = fma(d, d, rt); else if (r == TI - 1) rb = fma(d, d, rb); else rm = fma(d, d, rm);
                         if (k == 0) cl = fma(d, d, cl);
                         if (k == TJ - 1) cr = fma(d, d, cr);
                         phi[r][k] = nv;
                         po_[r] = old[r];
-                    }
-                    if (k == 0) {                 // sweep kdec = k - 2: converged?  (nothing of phi_{k-2} has been overwritten yet)
-                        const float err = total32(part_rd);
-                        if (kdec > a.itmax) return 2;
-                        if (converged(err, accq)) return 1;
                     }
                     if (has_tile) {
 #pragma unroll
@@ -1627,10 +1629,8 @@ __global__ void __launch_bounds__(T, MINB) mac_big_kernel(const MacArgs<R> a)
                 }
 #pragma unroll
                 for (int st = TJ; st < 5; st++) wsum += __shfl_xor_sync(0xffffffffu, wsum, 16 >> st);
-                R mid = R(0);
-#pragma unroll
-                for (int r = 1; r < TI - 1; r++) mid += rs[r];
-                const R acc0 = (TI > 1) ? fma(rs[0], w_top, fma(rs[TI - 1], w_bot, mid)) : rs[0] * (w_top + w_bot - R(1));
+                static_assert(TI > 1, "first and last tile row are distinct");
+                const R acc0 = fma(rt, w_top, fma(rb, w_bot, rm));
                 const R acc = fma(cl, w_lef, fma(cr, w_rig, acc0)) * w_has;
                 if ((tid & 31) == 0) part_wr[tid >> 5] = wsum;
                 __syncthreads();
