@@ -441,6 +441,25 @@ def test_generic_mac_kernel(monkeypatch, golden):
     assert "us" in env.fields          # the generic kernel keeps the starred velocities as state fields
 
 
+def test_rayleigh_on_the_large_grid_kernel():
+    """A 100x100 rayleigh cell takes the large-grid kernel (register-resident Poisson, fields in L2) in its rayleigh
+    instantiation — buoyancy term, segment temperatures, Neumann east wall in the residual — which the mixing tests
+    do not reach: one action from rest against the oracle, sweep counts exact."""
+    env = make("rayleigh", 2, init=False, L=2.0, H=2.0, n_sgts=5)
+    o = bo.rayleigh(init=False, L=2.0, H=2.0, n_sgts=5)
+    env.reset(); o.reset()
+    assert env.cfg.d["nx"] == 100 and env.cfg.d["ny"] == 100
+    a = np.random.default_rng(32).uniform(-1, 1, 5)
+    obs, rwd, d, t = env.step(torch.as_tensor(np.stack([a, -a])), want_iters=True)
+    ro = o.step(a)
+    assert int(env.last_iters[0, 0]) == int(o.last_iters.sum())
+    for f in ("u", "v", "p", "T"):
+        close(env.get_state(f)[0], getattr(o, f).reshape(-1), what=f"rayleigh 100x100 {f}")
+    close(obs[0], ro[0], what="obs")
+    close(rwd[:1], np.array([ro[1]]), rtol=1e-12, what="rwd")
+    assert int(env.status.max()) == 0
+
+
 def test_mac2d_sweep_counts_soak():
     """More seeds for the data-dependent Jacobi trip counts: the lagged, register-resident solvers must
     stop on exactly the sweep the reference stops on (one sweep more or less changes phi by ~1e-6)."""
