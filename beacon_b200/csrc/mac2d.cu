@@ -1229,6 +1229,9 @@ __device__ __noinline__ void transport_wavefront3(uint32_t offA, uint32_t offW, 
 // L2-resident global memory (Poisson is > 90 % of the work: ~65 sweeps per sub-step), transport in
 // row passes through the three-plane wavefront above.  One CTA per SM.
 // ---------------------------------------------------------------------------------------
+#ifndef MAC_BIG_COPYOUT_BY_TILE
+#define MAC_BIG_COPYOUT_BY_TILE 0
+#endif
 template <typename R, int NX, int NY, int TI, int TJ, int T, int MINB, bool DBG>
 __global__ void __launch_bounds__(T, MINB) mac_big_kernel(const MacArgs<R> a)
 {
@@ -1716,6 +1719,7 @@ __global__ void __launch_bounds__(T, MINB) mac_big_kernel(const MacArgs<R> a)
                     if (tid < 32) transport_wavefront3<R, NY>(0u, PLANE_B, 2 * PLANE_B, (ie - ib + 2) / 2, tid);
                     __syncthreads();
                     PHASE(5);
+#if MAC_BIG_COPYOUT_BY_TILE
                     if (mine) {
 #pragma unroll
                         for (int rp = 0; rp < TI; rp += 2)
@@ -1725,6 +1729,18 @@ __global__ void __launch_bounds__(T, MINB) mac_big_kernel(const MacArgs<R> a)
                                 s[o + rp * LD + k] = x.x; s[o + (rp + 1) * LD + k] = x.y;
                             }
                     }
+#else
+                    // the transported rows back to the plane, by ALL threads and row-contiguous (a warp writes 32
+                    // consecutive cells of one row: 2-3 cache lines instead of the ~10 a tile-wise store touches)
+                    {
+                        const R *AAs = AA;
+                        const int nrow = ie - ib + 1;
+                        for (int q = tid; q < nrow * NY; q += T) {
+                            const int ri = q / NY, j = 1 + q - ri * NY;
+                            s[(ib + ri) * LD + j] = AAs[(((ri >> 1) * RS + j) << 1) + (ri & 1)];
+                        }
+                    }
+#endif
                     __syncthreads();
                     PHASE(6);
                 }
