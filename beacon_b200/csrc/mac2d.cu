@@ -1232,6 +1232,9 @@ __device__ __noinline__ void transport_wavefront3(uint32_t offA, uint32_t offW, 
 #ifndef MAC_BIG_COPYOUT_BY_TILE
 #define MAC_BIG_COPYOUT_BY_TILE 0
 #endif
+#ifndef MAC_BIG_TRCOEF_BY_TILE
+#define MAC_BIG_TRCOEF_BY_TILE 0
+#endif
 template <typename R, int NX, int NY, int TI, int TJ, int T, int MINB, bool DBG>
 __global__ void __launch_bounds__(T, MINB) mac_big_kernel(const MacArgs<R> a)
 {
@@ -1690,6 +1693,7 @@ __global__ void __launch_bounds__(T, MINB) mac_big_kernel(const MacArgs<R> a)
                     // of rows high and passes start on tile boundaries): half the store instructions, conflict free
                     R2 *A2 = reinterpret_cast<R2 *>(AA) + ((i0 - ib) >> 1) * RS + j0, *W2 = reinterpret_cast<R2 *>(WW) + ((i0 - ib) >> 1) * RS + j0,
                        *S2 = reinterpret_cast<R2 *>(SS) + ((i0 - ib) >> 1) * RS + j0;
+#if MAC_BIG_TRCOEF_BY_TILE
                     if (mine) {
                         const R *uu = u + o, *vv = v + o, *sc = s + o;
 #pragma unroll
@@ -1714,6 +1718,44 @@ __global__ void __launch_bounds__(T, MINB) mac_big_kernel(const MacArgs<R> a)
                                 A2[(rp >> 1) * RS + k] = xa; W2[(rp >> 1) * RS + k] = xw; S2[(rp >> 1) * RS + k] = xs;
                             }
                     }
+#else
+                    // The coefficients are a pointwise function of old values, so for this phase the cells are dealt out
+                    // row-contiguous instead of by tile: a thread takes row-pair slots (rows i, i + 1 at column j) with
+                    // consecutive j across the lanes — every global load of u, v, C is coalesced (the tile-wise loads touched
+                    // ~10 cache lines per warp instruction) and all 512 threads work in both passes.
+                    {
+                        (void)mine; (void)A2; (void)W2; (void)S2;
+                        const int nslots = ((ie - ib + 2) >> 1) * NY;
+                        R2 *Ap = reinterpret_cast<R2 *>(AA), *Wp = reinterpret_cast<R2 *>(WW), *Sp = reinterpret_cast<R2 *>(SS);
+                        constexpr int TRIPS = ((PASS_ROWS / 2) * NY + T - 1) / T;
+#pragma unroll 3
+                        for (int n = 0; n < TRIPS; n++) {
+                            const int q = tid + n * T;
+                            if (q < nslots) {
+                                const int rp = q / NY, j = 1 + q - rp * NY, i = ib + 2 * rp;
+                                const R *uu = u + i * LD + j, *vv = v + i * LD + j, *sc = s + i * LD + j;
+                                const R u0 = uu[0], u1 = uu[LD], u2 = uu[2 * LD];
+                                const R v00 = vv[0], v01 = vv[1], v10 = vv[LD], v11 = vv[LD + 1];
+                                const R s00 = sc[0], s10 = sc[LD], s20 = sc[2 * LD], s01 = sc[1], s11 = sc[LD + 1];
+                                R2 xa, xw, xs;
+#pragma unroll
+                                for (int h = 0; h < 2; h++) {
+                                    const R uE = h ? u2 : u1, uW = h ? u1 : u0, vN = h ? v11 : v01, vS = h ? v10 : v00;
+                                    const R s0 = h ? s10 : s00, sE = h ? s20 : s10, sN = h ? s11 : s01;
+                                    R diff0 = ((sE - R(2) * s0) * a.inv_dx2 + (sN - R(2) * s0) * a.inv_dy2) * a.tcoef;
+                                    R conv0 = (uE * (R(0.5) * (sE + s0)) - uW * (R(0.5) * s0)) * inv_dx + (vN * (R(0.5) * (sN + s0)) - vS * (R(0.5) * s0)) * inv_dy;
+                                    R A = s0 + dt * (diff0 - conv0);
+                                    R BW = dt * (kx + R(0.5) * uW * inv_dx);
+                                    R BS = dt * (ky + R(0.5) * vS * inv_dy);
+                                    if (j == 1) { A = fma(BS, sc[h * LD - 1], A); BS = R(0); }                   // south ghost column
+                                    if (h == 0 && rp == 0) { A = fma(BW, sc[-LD], A); BW = R(0); }               // row west of the pass
+                                    if (h == 0) { xa.x = A; xw.x = BW; xs.x = BS; } else { xa.y = A; xw.y = BW; xs.y = BS; }
+                                }
+                                Ap[rp * RS + j] = xa; Wp[rp * RS + j] = xw; Sp[rp * RS + j] = xs;
+                            }
+                        }
+                    }
+#endif
                     __syncthreads();
                     PHASE(4);
                     if (tid < 32) transport_wavefront3<R, NY>(0u, PLANE_B, 2 * PLANE_B, (ie - ib + 2) / 2, tid);
