@@ -572,6 +572,9 @@ constexpr int mac_ldp(int ld, int ti) { int l = ld; while ((ti * l) % 16 != 2) l
 #else
 #define SWEEP_BARRIER() __syncthreads()
 #endif
+#ifndef MAC_REG_P_SCRATCH
+#define MAC_REG_P_SCRATCH 1
+#endif
 template <typename R, int NX, int NY, int TI, int TJ, int T, bool DBG>
 __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
 {
@@ -659,10 +662,18 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
         for (int j = LD; j < LDT; j++) S[e * LDT + j] = R(0);
     }
     __syncthreads();
-    // Ghost cells of p only ever accumulate the same increments as their wall-adjacent cells (phi
-    // ghosts are copies) and never feed back: they are brought up to date once, at the end of the
-    // launch, from the launch-initial values of the adjacent cells saved in the `us` workspace plane.
-    if (has_tile && (top || bot || lef || rig)) {
+    // The pressure stays in global memory (L2).  During the launch the authoritative copy of a thread's tile lives in a
+    // scratch laid out [cell][thread] (the `vs` workspace plane): a tile row is 5 doubles at an odd offset in the plane,
+    // so a tile-wise warp access touches ~13 cache lines, in the scratch consecutive lanes are contiguous (2 lines) and
+    // the neighbour tile's cell is the same slot 1 / TILES_J threads away.  The plane keeps the launch-initial values
+    // until the end: ghost cells of p only ever accumulate the same increments as their wall-adjacent cells (phi
+    // ghosts are copies) and never feed back, so they are brought up to date once, at the end of the launch.
+    constexpr bool PSC = MAC_REG_P_SCRATCH && TI * TJ * T <= N;
+    R *const sp = a.vs + row + tid;
+#define PSCR(r, k) sp[((r) * TJ + (k)) * T]
+    if (PSC) {
+        if (has_tile) { TILE_LOOP { PSCR(r, k) = gp[o + r * LD + k]; } }
+    } else if (has_tile && (top || bot || lef || rig)) {
         const R *p = gp + o;
         R *sv = a.us + row + o;
         TILE_LOOP { sv[r * LD + k] = p[r * LD + k]; }
@@ -747,7 +758,7 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
             TILE_LOOP {
                 const R2 *q = uv + r * LDU + k;
                 const R2 c = q[0], E = q[LDU], W = q[-LDU], Nn = q[1], Ss = q[-1];
-                const R uc = c.x, vc = c.y, pc = p[r * LD + k];
+                const R uc = c.x, vc = c.y, pc = PSC ? PSCR(r, k) : p[r * LD + k];
                 us[r][k] = R(0); vs[r][k] = R(0);
                 if (r > 0 || !top) {               // i >= 2
                     R uE = R(0.5) * (E.x + uc), uW = R(0.5) * (uc + W.x);
@@ -755,7 +766,8 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
                     R vN = R(0.5) * (Nn.y + q[-LDU + 1].y), vS = R(0.5) * (vc + W.y);
                     R conv = (uE * uE - uW * uW) * inv_dx + (uN * vN - uS * vS) * inv_dy;
                     R diff = ((E.x - R(2) * uc + W.x) * a.inv_dx2 + (Nn.x - R(2) * uc + Ss.x) * a.inv_dy2) * a.dcoef;
-                    R pres = (pc - p[r * LD + k - LD]) * inv_dx;
+                    const R pw = !PSC ? p[r * LD + k - LD] : (r > 0 ? PSCR(r - 1, k) : (sp - TILES_J)[((TI - 1) * TJ + k) * T]);
+                    R pres = (pc - pw) * inv_dx;
                     us[r][k] = diff - conv - pres;
                 }
                 if (k > 0 || !lef) {               // j >= 2
@@ -764,7 +776,8 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
                     R vN = R(0.5) * (Nn.y + vc), vS = R(0.5) * (vc + Ss.y);
                     R conv = (uE * vE - uW * vW) * inv_dx + (vN * vN - vS * vS) * inv_dy;
                     R diff = ((E.y - R(2) * vc + W.y) * a.inv_dx2 + (Nn.y - R(2) * vc + Ss.y) * a.inv_dy2) * a.dcoef;
-                    R pres = (pc - p[r * LD + k - 1]) * inv_dy;
+                    const R ps = !PSC ? p[r * LD + k - 1] : (k > 0 ? PSCR(r, k - 1) : (sp - 1)[(r * TJ + TJ - 1) * T]);
+                    R pres = (pc - ps) * inv_dy;
                     vs[r][k] = diff - conv - pres;
                 }
             }
@@ -1033,7 +1046,7 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
                 R *p = gp + o;
                 R2 *uv = UV + ou;
                 TILE_LOOP {
-                    p[r * LD + k] += phi[r][k];
+                    if (PSC) PSCR(r, k) += phi[r][k]; else p[r * LD + k] += phi[r][k];
                     R2 w = uv[r * LDU + k];
                     if (r > 0 || !top) { const R pw = (r > 0) ? phi[r - 1][k] : pf[-LDP + k]; w.x = w.x - dt * (phi[r][k] - pw) * inv_dx; }
                     if (k > 0 || !lef) { const R ps = (k > 0) ? phi[r][k - 1] : pf[r * LDP - 1]; w.y = w.y - dt * (phi[r][k] - ps) * inv_dy; }
@@ -1134,7 +1147,28 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
         const R2 w = UV[i * LDU + j];
         gu[e] = w.x; gv[e] = w.y; gs[e] = SS(i, j);
     }
-    if (has_tile && (top || bot || lef || rig)) {      // ghost cells of p += this launch's increments of the adjacent cell
+    if (PSC) {                                         // pressure back to its plane; ghost += adjacent(final) - adjacent(launch start)
+        if (has_tile) {
+            R *pp = gp + o;
+            if (top) {
+#pragma unroll
+                for (int k = 0; k < TJ; k++) pp[-LD + k] += PSCR(0, k) - pp[k];
+            }
+            if (bot) {
+#pragma unroll
+                for (int k = 0; k < TJ; k++) pp[TI * LD + k] += PSCR(TI - 1, k) - pp[(TI - 1) * LD + k];
+            }
+            if (lef) {
+#pragma unroll
+                for (int r = 0; r < TI; r++) pp[r * LD - 1] += PSCR(r, 0) - pp[r * LD];
+            }
+            if (rig) {
+#pragma unroll
+                for (int r = 0; r < TI; r++) pp[r * LD + TJ] += PSCR(r, TJ - 1) - pp[r * LD + TJ - 1];
+            }
+            TILE_LOOP { pp[r * LD + k] = PSCR(r, k); }
+        }
+    } else if (has_tile && (top || bot || lef || rig)) {      // ghost cells of p += this launch's increments of the adjacent cell
         R *p = gp + o;
         const R *sv = a.us + row + o;
         if (top) {
@@ -1158,6 +1192,7 @@ __global__ void __launch_bounds__(T, 2) mac_reg_kernel(const MacArgs<R> a)
     if (DBG && dbg) { for (int n = 0; n < (DBG ? 8 : 1); n++) a.dbg[n] += (unsigned long long)tph[n]; }
 #undef PHASE
 #undef TILE_LOOP
+#undef PSCR
 #undef UU
 #undef VV
 #undef SS
