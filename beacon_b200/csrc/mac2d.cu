@@ -556,7 +556,8 @@ __device__ __noinline__ bool residual_converged_exact(R mine, R *s_exact, R tol)
 //     writes its tile (+ the ghost copies it owns) to the other plane: one __syncthreads;
 //   * predictor output (us, vs) is staged in registers over one barrier and then overwrites U, V
 //     in place (old u, v are dead after the predictor; wall entries are 0 in both); the corrector
-//     is a pointwise in-place update; p stays in L2-resident global memory;
+//     is a pointwise in-place update; p stays in L2-resident global memory, in a thread-interleaved
+//     scratch ([cell][thread], coalesced) for the duration of a launch;
 //   * the first sweep (phi = 0) needs no halo: the exchange planes are never zeroed;
 //   * transport: A and B_W planes are written by all threads into the (then free) phi planes,
 //     B_S comes from V on the fly; ONE warp runs the recurrence over all rows in a single
