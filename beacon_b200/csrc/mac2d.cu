@@ -28,6 +28,15 @@
 //     update that only involves OLD values plus the coefficients multiplying the new neighbours;
 //     then one warp runs the remaining 2-FMA recurrence as a skewed wavefront, rows across lanes,
 //     the new west value travelling by warp shuffle (no barriers).
+//
+// Build switches (tuning aids; `python -m beacon_b200.build --tag=x -DNAME=1` + tools/ab.sh compare two libraries on the
+// same GPU box).  Each keeps the variant a measured change replaced, so that the A/B numbers of DESIGN.md 3.4 / 3.5 can
+// be reproduced; the product build defines none of them:
+//   MAC_REG_P_SCRATCH=0      rayleigh: pressure accessed tile-wise in its plane (47.0 k vs 50.7 k env-actions/s)
+//   MAC_BIG_DECIDE_LAST      mixing: convergence decision after the sweep, stores at its end (3.73 k vs 4.10 k)
+//   MAC_BIG_COPYOUT_BY_TILE  mixing: transported scalar copied back by tile (4.10 k vs 4.16 k)
+//   MAC_BIG_TRCOEF_BY_TILE   mixing: transport coefficients computed by tile (4.16 k vs 4.36 k)
+//   MAC_CLUSTER_BARRIER_TEST rayleigh: cluster barrier in place of the CTA barrier of a sweep (cost measurement)
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
